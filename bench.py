@@ -1,0 +1,424 @@
+#!/usr/bin/env python3
+"""bench.py - fosphor spectral hot path throughput on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (this repo's CUDA engine)
+  python bench.py --impl reference --gpus N --steps K ...  (the reference's own path)
+
+Workload = BASELINE.json configs[1]: N=1024 FFT, 256 power bins, overlap 4,
+continuous synthetic IQ, calls of B=1024 spectra.  One STEP is one display
+frame of the reference sink: 8 process calls (base_sink_c_impl.cc:133-146) =
+8192 spectra = 8.39 Mcomplex-samples entering the FFT.  The stream is the
+pre-overlapped one the reference's fosphor_cl_process() receives (overlap_cc
+upstream, lib/overlap_cc_impl.cc:64-79); the in-engine-overlap variant (raw
+stream, hop = N/4) is reported next to it under "overlap_in_engine".
+
+Metric: Mcomplex-samples/s into the FFT (whole job, all GPUs).  `value` is
+device-resident (inputs already in HBM, rotating over a pool larger than L2),
+`e2e` goes through the C ABI with HOST buffers: H2D of every sample and the
+D2H read-back of waterfall + histogram + spectrum each step inside the timed
+region.  Multi-GPU: one engine (one channel) per GPU, weak scaling, one NCCL
+max all-reduce of the max-hold trace per step (BASELINE.json configs[3]).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+N_FFT, N_BINS, OVERLAP, BATCH, CALLS_PER_STEP = 1024, 256, 4, 1024, 8
+WF_ROWS = 8192   # device ring holds one whole step so the FFT pass is one launch per step
+
+
+def algorithmic_bytes_per_call(n, k, b, r):
+    """SURVEY.md 8(d) / BASELINE.md 4: input + waterfall + histogram R/W + live/max R/W + window."""
+    return 8.0 * n * b * r + 4.0 * n * b + 8.0 * n * k + 32.0 * n + 4.0 * n
+
+
+def fft_kernel_bytes(n, spectra, r):
+    """dominant kernel (fft_power): cf32 in, f32 log-power out, window once"""
+    return (8.0 * r + 4.0) * n * spectra + 4.0 * n
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_stream_torch(torch, n_samples, seed, device):
+    """noise sigma=0.01 + 8 tones, generated on the device"""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    x = torch.randn((n_samples, 2), generator=g, device=device, dtype=torch.float32) * (0.01 / np.sqrt(2.0))
+    rng = np.random.default_rng(seed)
+    t = torch.arange(n_samples, device=device, dtype=torch.float32)
+    for f, a, p in zip(rng.uniform(-0.5, 0.5, 8), np.exp(rng.uniform(np.log(0.02), np.log(0.6), 8)),
+                       rng.uniform(0, 2 * np.pi, 8)):
+        ph = (t * float(f)) % 1.0 * (2 * np.pi) + float(p)
+        x[:, 0] += float(a) * torch.cos(ph)
+        x[:, 1] += float(a) * torch.sin(ph)
+    return x
+
+
+def cpu_baseline_port(seconds_budget=12.0):
+    """CPU oracle (f32 FFT variant, OpenMP over all host threads) on a bounded
+    sample of the same workload: whole steps of 8 calls x 1024 spectra."""
+    import oracle_lib
+    import signals
+    orc = oracle_lib.Oracle(fft_len=N_FFT, n_bins=N_BINS, wf_rows=1024, fft_f32=True)
+    x = signals.noise_tones(N_FFT * BATCH, seed=2).astype(np.complex64)
+    orc.process(x)                       # warm-up call
+    t0, calls = time.perf_counter(), 0
+    while True:
+        orc.process(x)
+        calls += 1
+        el = time.perf_counter() - t0
+        if (calls >= CALLS_PER_STEP and el > seconds_budget) or calls >= 64 * CALLS_PER_STEP:
+            break
+    orc.finish()
+    msps = calls * BATCH * N_FFT / el / 1e6
+    threads = oracle_lib.lib().fosphor_oracle_threads()
+    return {"value": msps, "unit": "Mcomplex-samples/s", "cores": int(threads), "kind": "port",
+            "sample": "%d calls of %d spectra (N=%d, K=%d), f32 FFT oracle, %.1f s" % (calls, BATCH, N_FFT, N_BINS, el)}
+
+
+def dist_setup(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return world, rank, local, dist
+
+
+def run_b200(args):
+    import torch
+    from gr_fosphor_b200.engine import Fosphor
+
+    world, rank, local, dist = dist_setup(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    peak, peak_src = measured_peaks()
+
+    n, k, b, calls = N_FFT, N_BINS, BATCH, CALLS_PER_STEP
+    spectra_per_step = calls * b
+    samples_per_step = spectra_per_step * n
+    hop = n // OVERLAP
+
+    eng = Fosphor(fft_len=n, n_bins=k, wf_rows=WF_ROWS, device=local, stream=stream.cuda_stream)
+
+    # ---- inputs: pre-overlapped pool (> L2) and a raw stream for the hop mode ----
+    pool_n = 6                                       # 6 x 64 MiB = 384 MiB > 126 MB L2
+    raw_len = (spectra_per_step - 1) * hop + n
+    raw_pool_n = 10                                  # 10 x 16 MiB = 168 MB of distinct raw data
+    raws = [synth_stream_torch(torch, raw_len, 1000 * rank + 2 + i, dev) for i in range(raw_pool_n)]
+    idx = (torch.arange(spectra_per_step, device=dev)[:, None] * hop + torch.arange(n, device=dev)[None, :]).reshape(-1)
+    pool = [raws[i][idx].contiguous() for i in range(pool_n)]     # what overlap_cc would emit
+    del idx
+    maxhold = torch.empty(n, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device(i, pre_overlapped=True):
+        if pre_overlapped:
+            eng.process_device_multi(pool[i % pool_n].data_ptr(), calls, b, n)
+        else:
+            eng.process_device_multi(raws[i % raw_pool_n].data_ptr(), calls, b, hop)
+        if dist is not None:                          # BASELINE configs[3]: reduced max-hold
+            eng.export_maxhold(maxhold.data_ptr())
+            dist.all_reduce(maxhold, op=dist.ReduceOp.MAX)
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident headline (clock sampling + per-kernel profiling) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    ms = timed(lambda i: step_device(i, True), args.steps, args.warmup)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    launches_timed = launches * args.steps // (args.steps + args.warmup)
+    value = world * args.steps * samples_per_step / (ms * 1e-3) / 1e6
+
+    # per-kernel durations: same loop again with event pairs around each launch
+    eng.profile(True)
+    timed(lambda i: step_device(i, True), args.steps, 1)
+    prof = eng.profile_read()
+    eng.profile(False)
+    fft_ms = prof["fft_ms"] / max(1, prof["fft_launches"])
+    acc_ms = prof["acc_ms"] / max(1, prof["acc_launches"])
+    fft_bytes = fft_kernel_bytes(n, spectra_per_step, 1.0)
+    achieved = fft_bytes / (fft_ms * 1e-3) / 1e9
+    step_bytes = calls * algorithmic_bytes_per_call(n, k, b, 1.0)
+
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "fft_power_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+
+    # ---- in-engine overlap variant (raw stream, hop = N/4) ----
+    ms_hop = timed(lambda i: step_device(i, False), args.steps, args.warmup)
+    value_hop = world * args.steps * samples_per_step / (ms_hop * 1e-3) / 1e6
+
+    # ---- e2e through the C ABI with host buffers ----
+    h_pool = [torch.empty((samples_per_step, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for hp, src in zip(h_pool, pool):
+        hp.copy_(src)
+    h_raw = [torch.empty((raw_len, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for hp, src in zip(h_raw, raws):
+        hp.copy_(src)
+    torch.cuda.synchronize()
+    call_len = b * n
+
+    def step_e2e(i):
+        base = h_pool[i % 2].data_ptr()
+        for c in range(calls):
+            eng.process_host_ptr(base + 8 * c * call_len, call_len)
+        if dist is not None:
+            eng.export_maxhold(maxhold.data_ptr())
+            dist.all_reduce(maxhold, op=dist.ReduceOp.MAX)
+        rc, _ = eng.finish()
+        assert rc == 1
+
+    def step_e2e_raw(i):
+        eng.process_host_raw_ptr(h_raw[i % 2].data_ptr(), calls, b, hop)
+        if dist is not None:
+            eng.export_maxhold(maxhold.data_ptr())
+            dist.all_reduce(maxhold, op=dist.ReduceOp.MAX)
+        rc, _ = eng.finish()
+        assert rc == 1
+
+    def timed_host(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fn(warmup + i)
+        torch.cuda.synchronize()
+        el = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([el], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        return el
+
+    e2e_steps = max(3, min(args.steps, 10))
+    eng_dev = eng
+    eng = Fosphor(fft_len=n, n_bins=k, wf_rows=1024, device=local, stream=stream.cuda_stream)   # reference-sized ring
+    ms_e2e = timed_host(step_e2e, e2e_steps, 3)
+    e2e = world * e2e_steps * samples_per_step / (ms_e2e * 1e-3) / 1e6
+    ms_e2e_raw = timed_host(step_e2e_raw, e2e_steps, 3)
+    e2e_raw = world * e2e_steps * samples_per_step / (ms_e2e_raw * 1e-3) / 1e6
+    d2h = 4 * (1024 * n + k * n + 4 * n)
+    eng.close()
+    eng = eng_dev
+
+    cpu = cpu_baseline_port() if (rank == 0 and world == 1 and not args.no_cpu) else None
+
+    if rank == 0:
+        out = {
+            "metric": "Mcomplex-samples/sec through FFT+histogram at N=1024",
+            "value": value, "unit": "Mcomplex-samples/s",
+            "spectra_per_s": value * 1e6 / n,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: N=1024, 256 bins, overlap=4 (pre-overlapped stream, r=1), "
+                                   "B=1024 spectra/call, step = 8 calls = 8192 spectra",
+                       "fft_len": n, "n_bins": k, "overlap": OVERLAP, "batch": b, "calls_per_step": calls,
+                       "wf_rows": WF_ROWS,
+                       "l2": "inputs rotate over a %d MiB pool (> 126 MB L2)" % (pool_n * samples_per_step * 8 // 2**20),
+                       "multi_gpu": "one channel per GPU, NCCL max all-reduce of max-hold per step" if world > 1 else "single"},
+            "gpu_launches": int(launches_timed),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "fft_power_kernel<Plan1024>",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": traffic,
+                         "bytes_per_launch": fft_bytes, "ms_per_launch": fft_ms,
+                         "accumulate_ms_per_launch": acc_ms,
+                         "step_algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                         "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+            "e2e": {"value": e2e, "unit": "Mcomplex-samples/s",
+                    "h2d_bytes_per_step": 8 * samples_per_step, "d2h_bytes_per_step": d2h,
+                    "api": "fosphor_cu_process_host x8 + fosphor_cu_finish (host pre-overlapped stream)"},
+            "overlap_in_engine": {"value": value_hop, "e2e": e2e_raw, "unit": "Mcomplex-samples/s",
+                                  "h2d_bytes_per_step": 8 * raw_len,
+                                  "note": "raw stream, hop=N/4 addressing inside the FFT kernel (r=1/4)"},
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's own path through its own API: the unmodified cl.c +
+    fft.cl + display.cl (oracle/_ref/libfosphor_ref.so) if an OpenCL device is
+    reachable on this box (it then runs on the same B200 through NVIDIA's OpenCL
+    - the box has no CPU OpenCL platform), else the CPU oracle port.  Host
+    buffers in, host results out (fosphor_process x8 + fosphor_cl_finish per
+    step).  The reference is hard-wired to 128 bins (display.cl:96)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import signals
+    n, b, calls = N_FFT, BATCH, CALLS_PER_STEP
+    raw = signals.noise_tones((calls * b - 1) * (n // OVERLAP) + n, seed=2)
+    x = signals.overlap_windows(raw, n, OVERLAP, calls * b).reshape(calls, b * n)
+    samples_per_step = calls * b * n
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libfosphor_ref.so")
+    kind, cores, eng = None, 1, None
+    if os.path.exists(ref_so):
+        try:
+            from gr_fosphor_b200.dropin import FosphorCL
+            eng = FosphorCL(ref_so)
+            kind = "reference"
+        except Exception as exc:                                   # no OpenCL here
+            sys.stderr.write("reference OpenCL path unavailable (%s); using the oracle port\n" % exc)
+    if eng is None:
+        import golden_cases
+        import oracle_lib
+        eng = golden_cases.OracleAdapter()
+        eng.o.close()
+        eng.o = oracle_lib.Oracle(fft_f32=True)
+        kind, cores = "port", int(oracle_lib.lib().fosphor_oracle_threads())
+
+    def step():
+        for c in range(calls):
+            assert eng.process(x[c]) == 0
+        assert eng.finish() == 1
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    value = args.steps * samples_per_step / el / 1e6
+    sample = ("%d steps of 8 calls x 1024 spectra, %s" %
+              (args.steps, "reference OpenCL kernels on the box's B200 via NVIDIA OpenCL (no CPU OpenCL platform exists), 128 bins"
+               if kind == "reference" else "CPU oracle port, f32 FFT, all host threads, 128 bins"))
+    out = {"impl": "reference", "metric": "Mcomplex-samples/sec through FFT+histogram at N=1024",
+           "value": value, "unit": "Mcomplex-samples/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "cfg2: N=1024, overlap=4 (pre-overlapped stream), B=1024 spectra/call, "
+                                  "step = 8 calls + finish; reference fixed at 128 bins"},
+           "cpu_baseline": {"value": value, "unit": "Mcomplex-samples/s", "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": value, "unit": "Mcomplex-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

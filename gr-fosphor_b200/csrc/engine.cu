@@ -1,0 +1,726 @@
+/*
+ * engine.cu - host side of libfosphor_b200.so: the parameterised fosphor_cu_*
+ * engine (include/fosphor_b200.h).  It plays the role of the reference's
+ * OpenCL host driver lib/fosphor/cl.c (state machine :95-99, buffer set-up
+ * :648-731, per-call enqueue :870-968, finish/read-back :970-1061) for CUDA:
+ * everything is enqueued on one stream, results stay in device arrays until
+ * finish().  The kernels live in fft_power.cuh and accumulate.cuh.
+ *
+ * No CPU fallback: if CUDA is unusable create() fails (-ENODEV / -EIO).
+ */
+#include <cerrno>
+#include <new>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/fosphor_b200.h"
+#include "accumulate.cuh"
+#include "fft_power.cuh"
+
+using namespace fosphor_b200;
+
+namespace {
+
+enum { ST_BOOTING = 0, ST_PENDING, ST_READY };   /* cl.c:95-99 */
+
+constexpr int N_TABLES = 8;      /* cached (weights, lut) sets, one per distinct batch size */
+constexpr int MAX_SPLITS = 64;
+
+struct BatchTables {
+	int batch = -1;
+	unsigned long long last_use = 0;
+	float *d_weights = nullptr;   /* [batch_max]      */
+	float2 *d_lut = nullptr;      /* [batch_max + 1]  */
+	float *h_stage = nullptr;     /* pinned: weights then lut */
+	cudaEvent_t uploaded = nullptr;
+	float carry = 0.0f;
+};
+
+} /* namespace */
+
+struct fosphor_cu {
+	fosphor_cu_params p;
+	int log2n = 0;
+	int device = 0;
+	int sm_count = 0;
+
+	cudaStream_t own_stream = nullptr;
+	cudaStream_t stream = nullptr;
+
+	float *d_win = nullptr;
+	float2 *d_tw = nullptr;
+	float *d_wf = nullptr;
+	float *d_hist = nullptr;
+	float2 *d_spec = nullptr;
+	unsigned *d_ghits = nullptr;
+	float *d_part_live = nullptr, *d_part_max = nullptr;
+	unsigned *d_tickets = nullptr;
+
+	/* host-sample staging (fosphor_cu_process_host*) */
+	size_t stage_elems = 0;              /* complex samples per slot */
+	float2 *h_in[2] = {nullptr, nullptr};
+	float2 *d_in[2] = {nullptr, nullptr};
+	cudaEvent_t in_done[2] = {nullptr, nullptr};
+	int slot = 0;
+	float *h_win = nullptr;              /* pinned copy of the window */
+	cudaEvent_t win_done = nullptr;
+
+	float histo_scale = 0.0f, histo_ofs = 0.0f;   /* cl.c:811 memset, :1087-1088 */
+	int wf_pos = 0;
+	int state = ST_BOOTING;
+
+	BatchTables tables[N_TABLES];
+	unsigned long long use_clock = 0;
+	unsigned long long launches = 0;
+
+	/* optional per-kernel timing (bench.py roofline): event pairs around launches */
+	bool profiling = false;
+	std::vector<cudaEvent_t> prof_ev[2][2];   /* [kernel: 0 fft, 1 accumulate][begin/end] */
+	size_t prof_used[2] = {0, 0};
+
+	char err[256] = {0};
+};
+
+namespace {
+
+int fail(fosphor_cu *e, int rc, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	if (e) {
+		vsnprintf(e->err, sizeof(e->err), fmt, ap);
+		fprintf(stderr, "[!] fosphor_b200: %s\n", e->err);   /* cl.c:109-114 style */
+	} else {
+		fprintf(stderr, "[!] fosphor_b200: ");
+		vfprintf(stderr, fmt, ap);
+		fprintf(stderr, "\n");
+	}
+	va_end(ap);
+	return rc;
+}
+
+#define CU_CHECK(e, call)                                                        \
+	do {                                                                     \
+		cudaError_t err__ = (call);                                      \
+		if (err__ != cudaSuccess)                                        \
+			return fail((e), -EIO, "CUDA error %d (%s) at %s:%d: %s", (int)err__, \
+			            cudaGetErrorString(err__), __FILE__, __LINE__, #call);    \
+	} while (0)
+
+/* ---- optional kernel timing ------------------------------------------------ */
+
+void prof_mark(fosphor_cu *e, int kernel, int end)
+{
+	if (!e->profiling)
+		return;
+	auto &v = e->prof_ev[kernel][end];
+	const size_t i = e->prof_used[kernel];
+	if (i >= v.size()) {
+		cudaEvent_t ev;
+		if (cudaEventCreate(&ev) != cudaSuccess)
+			return;
+		v.push_back(ev);
+	}
+	cudaEventRecord(v[i], e->stream);
+	if (end)
+		e->prof_used[kernel]++;
+}
+
+/* ---- FFT plan dispatch --------------------------------------------------- */
+
+template <class P>
+void build_twiddles(std::vector<float2> &tw)
+{
+	tw.resize(P::TW_ELEMS);
+	/* pass 1: tw[t][k] = exp(-2 pi i t k / (R0*R1)), k < R0 */
+	for (int t = 0; t < P::R1; t++)
+		for (int k = 0; k < P::R0; k++) {
+			const double a = -2.0 * M_PI * (double)t * (double)k / (double)(P::R0 * P::R1);
+			tw[t * P::R0 + k] = make_float2((float)cos(a), (float)sin(a));
+		}
+	if (P::NPASS == 3) {
+		const int p2 = P::R0 * P::R1;
+		for (int t = 0; t < P::R1; t++)
+			for (int k = 0; k < p2; k++) {
+				const double a = -2.0 * M_PI * (double)t * (double)k / (double)P::N;
+				tw[P::TW1 + t * p2 + k] = make_float2((float)cos(a), (float)sin(a));
+			}
+	}
+}
+
+template <class P>
+cudaError_t plan_setup()
+{
+	cudaError_t err = cudaFuncSetAttribute(fft_power_kernel<P, false>,
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM);
+	if (err != cudaSuccess)
+		return err;
+	return cudaFuncSetAttribute(fft_power_kernel<P, true>,
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM);
+}
+
+template <class P, bool CPLX>
+cudaError_t plan_launch(fosphor_cu *e, const float2 *in, long long hop, int wf_pos,
+                        float2 *cplx_out, int n_spectra)
+{
+	const int grid = (n_spectra + P::SPB - 1) / P::SPB;
+	prof_mark(e, 0, 0);
+	fft_power_kernel<P, CPLX><<<grid, P::THREADS, P::SMEM, e->stream>>>(
+		in, hop, e->d_win, e->d_tw, e->d_wf, wf_pos, e->p.wf_rows - 1, cplx_out, n_spectra);
+	prof_mark(e, 0, 1);
+	e->launches++;
+	return cudaGetLastError();
+}
+
+#define PLAN_SWITCH(n, EXPR)                                   \
+	switch (n) {                                           \
+	case 512:   { using P = Plan512;   EXPR; } break;      \
+	case 1024:  { using P = Plan1024;  EXPR; } break;      \
+	case 2048:  { using P = Plan2048;  EXPR; } break;      \
+	case 4096:  { using P = Plan4096;  EXPR; } break;      \
+	case 8192:  { using P = Plan8192;  EXPR; } break;      \
+	case 16384: { using P = Plan16384; EXPR; } break;      \
+	default: break;                                        \
+	}
+
+bool plan_supported(int n)
+{
+	return n == 512 || n == 1024 || n == 2048 || n == 4096 || n == 8192 || n == 16384;
+}
+
+cudaError_t launch_fft(fosphor_cu *e, const float2 *in, long long hop, int wf_pos, int n_spectra)
+{
+	cudaError_t err = cudaErrorInvalidValue;
+	PLAN_SWITCH(e->p.fft_len, (err = plan_launch<P, false>(e, in, hop, wf_pos, nullptr, n_spectra)));
+	return err;
+}
+
+/* ---- per-batch tables ---------------------------------------------------- */
+
+/* display.cl:150,210,241-245 evaluated once per distinct batch size on the
+ * host in f32 (same operation order as the reference / the oracle). */
+int get_tables(fosphor_cu *e, int batch, BatchTables **out)
+{
+	BatchTables *t = nullptr, *lru = &e->tables[0];
+	for (auto &c : e->tables) {
+		if (c.batch == batch)
+			t = &c;
+		if (c.last_use < lru->last_use)
+			lru = &c;
+	}
+	if (!t) {
+		t = lru;
+		const int bm = e->p.batch_max;
+		CU_CHECK(e, cudaEventSynchronize(t->uploaded));   /* staging free again */
+		float *w = t->h_stage;
+		float2 *lut = reinterpret_cast<float2 *>(t->h_stage + bm);
+		const float oma = 1.0f - e->p.live_alpha;         /* display.cl:99 */
+		const float fb = (float)batch;
+		const float rt0r = 1.0f / e->p.histo_t0r;
+		const float rt0d = 1.0f / e->p.histo_t0d;
+		for (int s = 0; s < batch; s++)
+			w[s] = powf(oma, (float)(batch - s - 1));
+		for (int hc = 0; hc <= batch; hc++) {
+			const float a = (float)hc / fb;
+			const float b = a * rt0r;
+			const float c = b + rt0d;
+			const float d = b * (1.0f / c);
+			lut[hc] = make_float2(d, powf(1.0f - c, fb));
+		}
+		t->carry = powf(oma, fb);
+		CU_CHECK(e, cudaMemcpyAsync(t->d_weights, w, sizeof(float) * batch,
+		                            cudaMemcpyHostToDevice, e->stream));
+		CU_CHECK(e, cudaMemcpyAsync(t->d_lut, lut, sizeof(float2) * (batch + 1),
+		                            cudaMemcpyHostToDevice, e->stream));
+		CU_CHECK(e, cudaEventRecord(t->uploaded, e->stream));
+		t->batch = batch;
+	}
+	t->last_use = ++e->use_clock;
+	*out = t;
+	return 0;
+}
+
+int choose_splits(const fosphor_cu *e, int batch, int *rows_per_split)
+{
+	const int tiles = e->p.fft_len / ACC_COLS;
+	const int target = 2 * e->sm_count;
+	int s = (target + tiles - 1) / tiles;
+	const int max_s = batch / 16 > 0 ? batch / 16 : 1;
+	if (s > max_s) s = max_s;
+	if (s > MAX_SPLITS) s = MAX_SPLITS;
+	if (s < 1) s = 1;
+	int rows = (batch + s - 1) / s;
+	rows = (rows + ACC_WARPS - 1) / ACC_WARPS * ACC_WARPS;
+	*rows_per_split = rows;
+	return (batch + rows - 1) / rows;
+}
+
+int launch_accumulate(fosphor_cu *e, int wf_pos, int batch)
+{
+	BatchTables *t;
+	int rc = get_tables(e, batch, &t);
+	if (rc)
+		return rc;
+
+	AccumArgs a;
+	a.wf = e->d_wf;
+	a.hist = e->d_hist;
+	a.spectrum = e->d_spec;
+	a.ghits = e->d_ghits;
+	a.part_live = e->d_part_live;
+	a.part_max = e->d_part_max;
+	a.tickets = e->d_tickets;
+	a.weights = t->d_weights;
+	a.lut = t->d_lut;
+	a.n = e->p.fft_len;
+	a.n_bins = e->p.n_bins;
+	a.wf_mask = e->p.wf_rows - 1;
+	a.wf_pos = wf_pos;
+	a.batch = batch;
+	a.splits = choose_splits(e, batch, &a.rows_per_split);
+	a.hscale = e->histo_scale;
+	a.hofs = e->histo_ofs;
+	a.alpha = e->p.live_alpha;
+	a.live_carry = t->carry;
+	a.mh_keep = e->p.maxhold_keep;
+	a.mh_mix = e->p.maxhold_mix;
+
+	const dim3 grid(e->p.fft_len / ACC_COLS, a.splits);
+	const size_t smem = sizeof(unsigned) * 32 * (size_t)e->p.n_bins;
+	prof_mark(e, 1, 0);
+	accumulate_kernel<<<grid, ACC_THREADS, smem, e->stream>>>(a);
+	prof_mark(e, 1, 1);
+	e->launches++;
+	CU_CHECK(e, cudaGetLastError());
+	return 0;
+}
+
+int clear_buffers(fosphor_cu *e)
+{
+	/* cl.c:406-465: spectrum (all 4N floats) and waterfall = -power.offset
+	 * (== -histo_ofs, fosphor.c:149-151), histogram = 0 */
+	const size_t n = e->p.fft_len;
+	const float nf = -e->histo_ofs;
+	fill_kernel<<<64, 256, 0, e->stream>>>(reinterpret_cast<float *>(e->d_spec), 4 * n, nf);
+	fill_kernel<<<4 * e->sm_count, 256, 0, e->stream>>>(e->d_wf, (size_t)e->p.wf_rows * n, nf);
+	e->launches += 2;
+	CU_CHECK(e, cudaGetLastError());
+	CU_CHECK(e, cudaMemsetAsync(e->d_hist, 0, sizeof(float) * (size_t)e->p.n_bins * n, e->stream));
+	return 0;
+}
+
+int validate_batch(const fosphor_cu *e, int n_spectra)
+{
+	/* cl.c:881-886 */
+	if (n_spectra < 0 || (n_spectra % e->p.batch_mult) || n_spectra > e->p.batch_max)
+		return -EINVAL;
+	return 0;
+}
+
+/* n_calls calls of `batch` spectra, input already on the device */
+int process_device_calls(fosphor_cu *e, const float2 *in, int n_calls, int batch, long long hop)
+{
+	if (validate_batch(e, batch) || n_calls < 0 || hop < 1)
+		return -EINVAL;
+	if (e->state == ST_BOOTING) {         /* cl.c:930-934 */
+		int rc = clear_buffers(e);
+		if (rc)
+			return rc;
+	}
+	if (batch > 0) {
+		const int calls_per_chunk = e->p.wf_rows / batch;    /* >= 1: wf_rows >= batch_max */
+		for (int c0 = 0; c0 < n_calls; c0 += calls_per_chunk) {
+			const int nc = n_calls - c0 < calls_per_chunk ? n_calls - c0 : calls_per_chunk;
+			CU_CHECK(e, launch_fft(e, in + (long long)c0 * batch * hop, hop, e->wf_pos, nc * batch));
+			for (int c = 0; c < nc; c++) {
+				int rc = launch_accumulate(e, e->wf_pos, batch);
+				if (rc)
+					return rc;
+				e->wf_pos = (e->wf_pos + batch) & (e->p.wf_rows - 1);   /* cl.c:954 */
+			}
+		}
+	}
+	e->state = ST_PENDING;                /* cl.c:957 */
+	return 0;
+}
+
+int upload_staged(fosphor_cu *e, const float2 *src, size_t n_samples, float2 **dev_out)
+{
+	const int s = e->slot;
+	e->slot ^= 1;
+	CU_CHECK(e, cudaEventSynchronize(e->in_done[s]));
+	memcpy(e->h_in[s], src, sizeof(float2) * n_samples);
+	CU_CHECK(e, cudaMemcpyAsync(e->d_in[s], e->h_in[s], sizeof(float2) * n_samples,
+	                            cudaMemcpyHostToDevice, e->stream));
+	CU_CHECK(e, cudaEventRecord(e->in_done[s], e->stream));
+	*dev_out = e->d_in[s];
+	return 0;
+}
+
+} /* namespace */
+
+/* ------------------------------------------------------------------------ */
+/* C ABI                                                                     */
+/* ------------------------------------------------------------------------ */
+
+extern "C" {
+
+void fosphor_cu_default_params(struct fosphor_cu_params *p)
+{
+	p->fft_len = 1024;          /* private.h:21-22 */
+	p->n_bins = 128;            /* display.cl:96 */
+	p->wf_rows = 1024;          /* cl.c:430-432 */
+	p->batch_mult = 16;         /* private.h:24 */
+	p->batch_max = 1024;        /* private.h:25 */
+	p->histo_t0r = 16.0f;       /* cl.c:714 */
+	p->histo_t0d = 1024.0f;     /* cl.c:715 */
+	p->live_alpha = 0.002f;     /* cl.c:716 */
+	p->maxhold_keep = 0.999f;   /* display.cl:303 */
+	p->maxhold_mix = 0.001f;
+	p->device = -1;
+}
+
+void fosphor_cu_destroy(struct fosphor_cu *e)
+{
+	if (!e)
+		return;
+	if (e->stream)
+		cudaStreamSynchronize(e->stream);
+	cudaFree(e->d_win); cudaFree(e->d_tw); cudaFree(e->d_wf); cudaFree(e->d_hist);
+	cudaFree(e->d_spec); cudaFree(e->d_ghits); cudaFree(e->d_part_live);
+	cudaFree(e->d_part_max); cudaFree(e->d_tickets);
+	for (int i = 0; i < 2; i++) {
+		cudaFreeHost(e->h_in[i]);
+		cudaFree(e->d_in[i]);
+		if (e->in_done[i]) cudaEventDestroy(e->in_done[i]);
+	}
+	cudaFreeHost(e->h_win);
+	if (e->win_done) cudaEventDestroy(e->win_done);
+	for (auto &t : e->tables) {
+		cudaFree(t.d_weights); cudaFree(t.d_lut); cudaFreeHost(t.h_stage);
+		if (t.uploaded) cudaEventDestroy(t.uploaded);
+	}
+	for (int k = 0; k < 2; k++)
+		for (int j = 0; j < 2; j++)
+			for (cudaEvent_t ev : e->prof_ev[k][j])
+				cudaEventDestroy(ev);
+	if (e->own_stream) cudaStreamDestroy(e->own_stream);
+	delete e;
+}
+
+int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *pp)
+{
+	if (!out || !pp)
+		return -EINVAL;
+	*out = nullptr;
+	const fosphor_cu_params &p = *pp;
+	if (!plan_supported(p.fft_len) || p.n_bins < 2 || p.n_bins > 4096 ||
+	    p.wf_rows < 1 || (p.wf_rows & (p.wf_rows - 1)) ||
+	    p.batch_mult < 1 || p.batch_max < p.batch_mult || p.batch_max % p.batch_mult ||
+	    p.wf_rows < p.batch_max || !(p.histo_t0r > 0.0f) || !(p.histo_t0d > 0.0f))
+		return fail(nullptr, -EINVAL, "unsupported engine parameters (N=%d K=%d W=%d batch %d/%d)",
+		            p.fft_len, p.n_bins, p.wf_rows, p.batch_mult, p.batch_max);
+
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+		return fail(nullptr, -ENODEV, "no CUDA device (this library has no CPU fallback)");
+
+	fosphor_cu *e = new (std::nothrow) fosphor_cu;
+	if (!e)
+		return -ENOMEM;
+	e->p = p;
+	e->log2n = ilog2c(p.fft_len);
+
+#define CREATE_CHECK(call)                                                         \
+	do {                                                                       \
+		cudaError_t err__ = (call);                                        \
+		if (err__ != cudaSuccess) {                                        \
+			int rc__ = fail(e, err__ == cudaErrorMemoryAllocation ? -ENOMEM : -EIO, \
+			                "CUDA error %d (%s) at %s:%d: %s", (int)err__,  \
+			                cudaGetErrorString(err__), __FILE__, __LINE__, #call); \
+			fosphor_cu_destroy(e);                                     \
+			return rc__;                                               \
+		}                                                                  \
+	} while (0)
+
+	if (p.device >= 0)
+		CREATE_CHECK(cudaSetDevice(p.device));
+	CREATE_CHECK(cudaGetDevice(&e->device));
+	cudaDeviceProp prop;
+	CREATE_CHECK(cudaGetDeviceProperties(&prop, e->device));
+	if (prop.major < 10) {
+		fail(e, -ENODEV, "device %s is sm_%d%d; this library is built for sm_100a only",
+		     prop.name, prop.major, prop.minor);
+		fosphor_cu_destroy(e);
+		return -ENODEV;
+	}
+	e->sm_count = prop.multiProcessorCount;
+	CREATE_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+	e->stream = e->own_stream;
+
+	const size_t n = p.fft_len, k = p.n_bins, w = p.wf_rows;
+	CREATE_CHECK(cudaMalloc(&e->d_win, sizeof(float) * n));
+	CREATE_CHECK(cudaMalloc(&e->d_wf, sizeof(float) * w * n));
+	CREATE_CHECK(cudaMalloc(&e->d_hist, sizeof(float) * k * n));
+	CREATE_CHECK(cudaMalloc(&e->d_spec, sizeof(float2) * 2 * n));
+	CREATE_CHECK(cudaMalloc(&e->d_ghits, sizeof(unsigned) * k * n));
+	CREATE_CHECK(cudaMalloc(&e->d_part_live, sizeof(float) * MAX_SPLITS * n));
+	CREATE_CHECK(cudaMalloc(&e->d_part_max, sizeof(float) * MAX_SPLITS * n));
+	CREATE_CHECK(cudaMalloc(&e->d_tickets, sizeof(unsigned) * (n / ACC_COLS)));
+	CREATE_CHECK(cudaMemset(e->d_ghits, 0, sizeof(unsigned) * k * n));
+	CREATE_CHECK(cudaMemset(e->d_tickets, 0, sizeof(unsigned) * (n / ACC_COLS)));
+	CREATE_CHECK(cudaMemset(e->d_hist, 0, sizeof(float) * k * n));
+	CREATE_CHECK(cudaMemset(e->d_wf, 0, sizeof(float) * w * n));
+	CREATE_CHECK(cudaMemset(e->d_spec, 0, sizeof(float2) * 2 * n));
+
+	/* window defaults to all ones until one is loaded (cl.c leaves it undefined) */
+	CREATE_CHECK(cudaMallocHost(&e->h_win, sizeof(float) * n));
+	CREATE_CHECK(cudaEventCreateWithFlags(&e->win_done, cudaEventDisableTiming));
+	for (size_t i = 0; i < n; i++)
+		e->h_win[i] = 1.0f;
+	CREATE_CHECK(cudaMemcpy(e->d_win, e->h_win, sizeof(float) * n, cudaMemcpyHostToDevice));
+
+	{
+		std::vector<float2> tw;
+		PLAN_SWITCH(p.fft_len, build_twiddles<P>(tw));
+		CREATE_CHECK(cudaMalloc(&e->d_tw, sizeof(float2) * tw.size()));
+		CREATE_CHECK(cudaMemcpy(e->d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+		cudaError_t perr = cudaErrorInvalidValue;
+		PLAN_SWITCH(p.fft_len, (perr = plan_setup<P>()));
+		CREATE_CHECK(perr);
+	}
+	CREATE_CHECK(cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                                  (int)(sizeof(unsigned) * 32 * k)));
+
+	for (auto &t : e->tables) {
+		CREATE_CHECK(cudaMalloc(&t.d_weights, sizeof(float) * p.batch_max));
+		CREATE_CHECK(cudaMalloc(&t.d_lut, sizeof(float2) * (p.batch_max + 1)));
+		CREATE_CHECK(cudaMallocHost(&t.h_stage, sizeof(float) * p.batch_max + sizeof(float2) * (p.batch_max + 1)));
+		CREATE_CHECK(cudaEventCreateWithFlags(&t.uploaded, cudaEventDisableTiming));
+	}
+
+	e->stage_elems = (size_t)p.batch_max * n;
+	for (int i = 0; i < 2; i++) {
+		CREATE_CHECK(cudaMallocHost(&e->h_in[i], sizeof(float2) * e->stage_elems));
+		CREATE_CHECK(cudaMalloc(&e->d_in[i], sizeof(float2) * e->stage_elems));
+		CREATE_CHECK(cudaEventCreateWithFlags(&e->in_done[i], cudaEventDisableTiming));
+	}
+#undef CREATE_CHECK
+
+	*out = e;
+	return 0;
+}
+
+int fosphor_cu_set_stream(struct fosphor_cu *e, void *cuda_stream)
+{
+	if (!e)
+		return -EINVAL;
+	CU_CHECK(e, cudaStreamSynchronize(e->stream));
+	e->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+	return 0;
+}
+
+int fosphor_cu_load_fft_window(struct fosphor_cu *e, const float *win_host)
+{
+	if (!e || !win_host)
+		return -EINVAL;
+	CU_CHECK(e, cudaEventSynchronize(e->win_done));
+	memcpy(e->h_win, win_host, sizeof(float) * e->p.fft_len);
+	CU_CHECK(e, cudaMemcpyAsync(e->d_win, e->h_win, sizeof(float) * e->p.fft_len,
+	                            cudaMemcpyHostToDevice, e->stream));
+	CU_CHECK(e, cudaEventRecord(e->win_done, e->stream));
+	return 0;
+}
+
+int fosphor_cu_set_histogram_range(struct fosphor_cu *e, float scale, float offset)
+{
+	if (!e)
+		return -EINVAL;
+	e->histo_scale = scale * (float)e->p.n_bins;    /* cl.c:1087 */
+	e->histo_ofs = offset;
+	return 0;
+}
+
+int fosphor_cu_process_device(struct fosphor_cu *e, const void *samples_dev,
+                              int n_spectra, long long hop)
+{
+	if (!e || (!samples_dev && n_spectra > 0))
+		return -EINVAL;
+	return process_device_calls(e, static_cast<const float2 *>(samples_dev), 1, n_spectra, hop);
+}
+
+int fosphor_cu_process_device_multi(struct fosphor_cu *e, const void *samples_dev,
+                                    int n_calls, int batch, long long hop)
+{
+	if (!e || (!samples_dev && n_calls > 0 && batch > 0))
+		return -EINVAL;
+	return process_device_calls(e, static_cast<const float2 *>(samples_dev), n_calls, batch, hop);
+}
+
+int fosphor_cu_process_host(struct fosphor_cu *e, const void *samples_host, int len)
+{
+	if (!e)
+		return -EINVAL;
+	const int n = e->p.fft_len;
+	/* cl.c:881-886 */
+	if (len < 0 || (len % (e->p.batch_mult * n)) || len > e->p.batch_max * n)
+		return -EINVAL;
+	if (len > 0 && !samples_host)
+		return -EINVAL;
+	float2 *dev = nullptr;
+	if (len > 0) {
+		int rc = upload_staged(e, static_cast<const float2 *>(samples_host), (size_t)len, &dev);
+		if (rc)
+			return rc;
+	}
+	return process_device_calls(e, dev, 1, len / n, n);
+}
+
+int fosphor_cu_process_host_raw(struct fosphor_cu *e, const void *raw_host,
+                                int n_calls, int batch, long long hop)
+{
+	if (!e || validate_batch(e, batch) || n_calls < 0 || hop < 1 || hop > e->p.fft_len)
+		return -EINVAL;
+	if (n_calls == 0 || batch == 0)
+		return process_device_calls(e, nullptr, n_calls, batch, hop);
+	if (!raw_host)
+		return -EINVAL;
+	const float2 *raw = static_cast<const float2 *>(raw_host);
+	const long long n = e->p.fft_len;
+	/* calls per staged chunk: (c*batch - 1)*hop + N <= stage_elems */
+	long long cpc = (((long long)e->stage_elems - n) / hop + 1) / batch;
+	if (cpc < 1)
+		cpc = 1;    /* batch*hop <= batch_max*N always fits one call */
+	for (long long c0 = 0; c0 < n_calls; c0 += cpc) {
+		const long long nc = n_calls - c0 < cpc ? n_calls - c0 : cpc;
+		const size_t samples = (size_t)((nc * batch - 1) * hop + n);
+		float2 *dev = nullptr;
+		int rc = upload_staged(e, raw + c0 * batch * hop, samples, &dev);
+		if (rc)
+			return rc;
+		rc = process_device_calls(e, dev, (int)nc, batch, hop);
+		if (rc)
+			return rc;
+	}
+	return 0;
+}
+
+int fosphor_cu_finish(struct fosphor_cu *e, float *waterfall_host,
+                      float *histogram_host, float *spectrum_host)
+{
+	if (!e)
+		return -EINVAL;
+	if (e->state == ST_READY)             /* cl.c:978-979 */
+		return 0;
+	if (e->state == ST_BOOTING) {         /* cl.c:982-994 */
+		int rc = clear_buffers(e);
+		if (rc)
+			return rc;
+	}
+	const size_t n = e->p.fft_len;
+	/* cl.c:1012-1048 */
+	if (waterfall_host)
+		CU_CHECK(e, cudaMemcpyAsync(waterfall_host, e->d_wf, sizeof(float) * e->p.wf_rows * n,
+		                            cudaMemcpyDeviceToHost, e->stream));
+	if (histogram_host)
+		CU_CHECK(e, cudaMemcpyAsync(histogram_host, e->d_hist, sizeof(float) * e->p.n_bins * n,
+		                            cudaMemcpyDeviceToHost, e->stream));
+	if (spectrum_host)
+		CU_CHECK(e, cudaMemcpyAsync(spectrum_host, e->d_spec, sizeof(float2) * 2 * n,
+		                            cudaMemcpyDeviceToHost, e->stream));
+	CU_CHECK(e, cudaStreamSynchronize(e->stream));   /* cl.c:1052 */
+	e->state = ST_READY;
+	return 1;
+}
+
+int fosphor_cu_sync(struct fosphor_cu *e)
+{
+	if (!e)
+		return -EINVAL;
+	CU_CHECK(e, cudaStreamSynchronize(e->stream));
+	return 0;
+}
+
+int fosphor_cu_get_waterfall_position(const struct fosphor_cu *e)
+{
+	return e ? e->wf_pos : -EINVAL;       /* cl.c:1073-1079 */
+}
+
+float *fosphor_cu_device_waterfall(struct fosphor_cu *e) { return e ? e->d_wf : nullptr; }
+float *fosphor_cu_device_histogram(struct fosphor_cu *e) { return e ? e->d_hist : nullptr; }
+float *fosphor_cu_device_spectrum(struct fosphor_cu *e)
+{
+	return e ? reinterpret_cast<float *>(e->d_spec) : nullptr;
+}
+
+int fosphor_cu_export_maxhold(struct fosphor_cu *e, float *out_dev)
+{
+	if (!e || !out_dev)
+		return -EINVAL;
+	const int n = e->p.fft_len;
+	export_maxhold_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_spec, n, out_dev);
+	e->launches++;
+	CU_CHECK(e, cudaGetLastError());
+	return 0;
+}
+
+int fosphor_cu_debug_fft(struct fosphor_cu *e, const void *samples_dev,
+                         int n_spectra, long long hop, void *out_dev)
+{
+	if (!e || !samples_dev || !out_dev || n_spectra < 0 || hop < 1)
+		return -EINVAL;
+	cudaError_t err = cudaErrorInvalidValue;
+	PLAN_SWITCH(e->p.fft_len, (err = plan_launch<P, true>(e, static_cast<const float2 *>(samples_dev), hop, 0,
+	                                                      static_cast<float2 *>(out_dev), n_spectra)));
+	CU_CHECK(e, err);
+	return 0;
+}
+
+int fosphor_cu_profile(struct fosphor_cu *e, int enable)
+{
+	if (!e)
+		return -EINVAL;
+	CU_CHECK(e, cudaStreamSynchronize(e->stream));
+	e->profiling = enable != 0;
+	e->prof_used[0] = e->prof_used[1] = 0;
+	return 0;
+}
+
+int fosphor_cu_profile_read(struct fosphor_cu *e, double *fft_ms, unsigned long long *fft_launches,
+                            double *acc_ms, unsigned long long *acc_launches)
+{
+	if (!e)
+		return -EINVAL;
+	CU_CHECK(e, cudaStreamSynchronize(e->stream));
+	double ms[2] = {0.0, 0.0};
+	for (int k = 0; k < 2; k++)
+		for (size_t i = 0; i < e->prof_used[k]; i++) {
+			float t = 0.0f;
+			CU_CHECK(e, cudaEventElapsedTime(&t, e->prof_ev[k][0][i], e->prof_ev[k][1][i]));
+			ms[k] += t;
+		}
+	if (fft_ms) *fft_ms = ms[0];
+	if (fft_launches) *fft_launches = e->prof_used[0];
+	if (acc_ms) *acc_ms = ms[1];
+	if (acc_launches) *acc_launches = e->prof_used[1];
+	e->prof_used[0] = e->prof_used[1] = 0;
+	return 0;
+}
+
+unsigned long long fosphor_cu_launch_count(const struct fosphor_cu *e)
+{
+	return e ? e->launches : 0;
+}
+
+const char *fosphor_cu_last_error(const struct fosphor_cu *e)
+{
+	return e ? e->err : "null engine";
+}
+
+} /* extern "C" */

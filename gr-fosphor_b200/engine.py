@@ -1,0 +1,206 @@
+"""ctypes mirror of the parameterised ``fosphor_cu_*`` C ABI
+(include/fosphor_b200.h) - test / bench harness only; the product is
+``libfosphor_b200.so``.  There is no fallback: if the library is missing or no
+CUDA device is usable, construction raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class Params(C.Structure):
+    """``struct fosphor_cu_params``"""
+    _fields_ = [("fft_len", C.c_int), ("n_bins", C.c_int), ("wf_rows", C.c_int),
+                ("batch_mult", C.c_int), ("batch_max", C.c_int),
+                ("histo_t0r", C.c_float), ("histo_t0d", C.c_float), ("live_alpha", C.c_float),
+                ("maxhold_keep", C.c_float), ("maxhold_mix", C.c_float), ("device", C.c_int)]
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load libfosphor_b200.so (the in-tree build).  Raises if it is absent:
+    the product path never runs without the CUDA library."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _build.LIB
+    if not os.path.exists(path):
+        raise RuntimeError("%s not built - run `python __graft_entry__.py` / build()" % path)
+    L = C.CDLL(path)
+    vp, ll = C.c_void_p, C.c_longlong
+    L.fosphor_cu_default_params.argtypes = [C.POINTER(Params)]
+    L.fosphor_cu_default_params.restype = None
+    L.fosphor_cu_create.argtypes = [C.POINTER(vp), C.POINTER(Params)]
+    L.fosphor_cu_destroy.argtypes = [vp]
+    L.fosphor_cu_destroy.restype = None
+    L.fosphor_cu_set_stream.argtypes = [vp, vp]
+    L.fosphor_cu_load_fft_window.argtypes = [vp, vp]
+    L.fosphor_cu_set_histogram_range.argtypes = [vp, C.c_float, C.c_float]
+    L.fosphor_cu_process_host.argtypes = [vp, vp, C.c_int]
+    L.fosphor_cu_process_device.argtypes = [vp, vp, C.c_int, ll]
+    L.fosphor_cu_process_device_multi.argtypes = [vp, vp, C.c_int, C.c_int, ll]
+    L.fosphor_cu_process_host_raw.argtypes = [vp, vp, C.c_int, C.c_int, ll]
+    L.fosphor_cu_finish.argtypes = [vp, vp, vp, vp]
+    L.fosphor_cu_sync.argtypes = [vp]
+    L.fosphor_cu_get_waterfall_position.argtypes = [vp]
+    for n in ("waterfall", "histogram", "spectrum"):
+        f = getattr(L, "fosphor_cu_device_" + n)
+        f.argtypes = [vp]
+        f.restype = vp
+    L.fosphor_cu_export_maxhold.argtypes = [vp, vp]
+    L.fosphor_cu_debug_fft.argtypes = [vp, vp, C.c_int, ll, vp]
+    L.fosphor_cu_profile.argtypes = [vp, C.c_int]
+    L.fosphor_cu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong),
+                                          C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
+    L.fosphor_cu_launch_count.argtypes = [vp]
+    L.fosphor_cu_launch_count.restype = C.c_ulonglong
+    L.fosphor_cu_last_error.argtypes = [vp]
+    L.fosphor_cu_last_error.restype = C.c_char_p
+    if path == _build.LIB:
+        _lib = L
+    return L
+
+
+def default_window(n):
+    """lib/fosphor/fosphor.c:113-118 generalised to N (f32 arithmetic)."""
+    f = np.float32
+    i = np.arange(n, dtype=np.float32)
+    arg = (f(2.0) * f(3.141592) * i) / f(n)
+    return ((f(0.54) - f(0.46) * np.cos(arg, dtype=np.float32)) * f(1.855)).astype(np.float32)
+
+
+def power_range(n, db_ref, db_per_div):
+    """lib/fosphor/fosphor.c:131-152 -> (scale, offset) f32, with k = log10(N)."""
+    f = np.float32
+    db0 = db_ref - 10 * db_per_div
+    k = np.log10(f(n), dtype=np.float32)
+    return f(f(20.0) / f(db_ref - db0)), f(-(k + f(db0) / f(20.0)))
+
+
+class Fosphor:
+    """One engine instance == one fosphor display (one channel)."""
+
+    def __init__(self, fft_len=1024, n_bins=128, wf_rows=1024, batch_mult=16, batch_max=1024,
+                 t0r=16.0, t0d=1024.0, alpha=0.002, device=-1, window=None,
+                 db_ref=0, db_per_div=10, stream=None):
+        self.lib = load_library()
+        p = Params()
+        self.lib.fosphor_cu_default_params(C.byref(p))
+        p.fft_len, p.n_bins, p.wf_rows = fft_len, n_bins, wf_rows
+        p.batch_mult, p.batch_max = batch_mult, batch_max
+        p.histo_t0r, p.histo_t0d, p.live_alpha = t0r, t0d, alpha
+        p.device = device
+        self.p = p
+        self.n, self.k, self.w = fft_len, n_bins, wf_rows
+        self.h = C.c_void_p()
+        rc = self.lib.fosphor_cu_create(C.byref(self.h), C.byref(p))
+        if rc:
+            self.h = None
+            raise RuntimeError("fosphor_cu_create failed: %d" % rc)
+        if stream is not None:
+            self.set_stream(stream)
+        self.load_fft_window(default_window(fft_len) if window is None else window)
+        self.set_power_range(db_ref, db_per_div)
+
+    def _chk(self, rc):
+        if rc < 0 and rc != -22:
+            raise RuntimeError("fosphor_b200 error %d: %s" % (rc, self.lib.fosphor_cu_last_error(self.h).decode()))
+        return rc
+
+    def set_stream(self, stream):
+        return self._chk(self.lib.fosphor_cu_set_stream(self.h, C.c_void_p(int(stream) if stream else 0)))
+
+    def load_fft_window(self, win):
+        win = np.ascontiguousarray(win, np.float32)
+        assert win.shape == (self.n,)
+        return self._chk(self.lib.fosphor_cu_load_fft_window(self.h, win.ctypes.data))
+
+    def set_power_range(self, db_ref, db_per_div):
+        s, o = power_range(self.n, db_ref, db_per_div)
+        return self.set_histogram_range(s, o)
+
+    def set_histogram_range(self, scale, offset):
+        return self._chk(self.lib.fosphor_cu_set_histogram_range(self.h, float(scale), float(offset)))
+
+    def process(self, samples):
+        """Host cf32 samples, pre-overlapped windows (reference contract)."""
+        x = np.ascontiguousarray(samples, np.complex64)
+        return self._chk(self.lib.fosphor_cu_process_host(self.h, x.ctypes.data, x.size))
+
+    def process_host_ptr(self, ptr, length):
+        return self._chk(self.lib.fosphor_cu_process_host(self.h, C.c_void_p(ptr), int(length)))
+
+    def process_host_raw(self, raw, n_calls, batch, hop):
+        x = np.ascontiguousarray(raw, np.complex64)
+        assert n_calls * batch == 0 or (n_calls * batch - 1) * hop + self.n <= x.size
+        return self._chk(self.lib.fosphor_cu_process_host_raw(self.h, x.ctypes.data, n_calls, batch, hop))
+
+    def process_host_raw_ptr(self, ptr, n_calls, batch, hop):
+        return self._chk(self.lib.fosphor_cu_process_host_raw(self.h, C.c_void_p(ptr), n_calls, batch, hop))
+
+    def process_device(self, dev_ptr, n_spectra, hop=None):
+        return self._chk(self.lib.fosphor_cu_process_device(
+            self.h, C.c_void_p(dev_ptr), n_spectra, self.n if hop is None else hop))
+
+    def process_device_multi(self, dev_ptr, n_calls, batch, hop=None):
+        return self._chk(self.lib.fosphor_cu_process_device_multi(
+            self.h, C.c_void_p(dev_ptr), n_calls, batch, self.n if hop is None else hop))
+
+    def finish(self, want=("waterfall", "histogram", "spectrum")):
+        """Returns (rc, dict of host arrays); arrays only refreshed when rc == 1."""
+        if not hasattr(self, "_host"):
+            self._host = {"waterfall": np.zeros((self.w, self.n), np.float32),
+                          "histogram": np.zeros((self.k, self.n), np.float32),
+                          "spectrum": np.zeros((2, self.n, 2), np.float32)}
+        ptrs = [self._host[k].ctypes.data if k in want else None
+                for k in ("waterfall", "histogram", "spectrum")]
+        rc = self._chk(self.lib.fosphor_cu_finish(self.h, *ptrs))
+        return rc, self._host
+
+    def sync(self):
+        return self._chk(self.lib.fosphor_cu_sync(self.h))
+
+    @property
+    def waterfall_position(self):
+        return self.lib.fosphor_cu_get_waterfall_position(self.h)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.fosphor_cu_launch_count(self.h))
+
+    def profile(self, enable=True):
+        return self._chk(self.lib.fosphor_cu_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        a, b = C.c_double(), C.c_double()
+        na, nb = C.c_ulonglong(), C.c_ulonglong()
+        self._chk(self.lib.fosphor_cu_profile_read(self.h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
+        return {"fft_ms": a.value, "fft_launches": na.value, "acc_ms": b.value, "acc_launches": nb.value}
+
+    def device_ptrs(self):
+        return {n: getattr(self.lib, "fosphor_cu_device_" + n)(self.h)
+                for n in ("waterfall", "histogram", "spectrum")}
+
+    def export_maxhold(self, out_dev_ptr):
+        return self._chk(self.lib.fosphor_cu_export_maxhold(self.h, C.c_void_p(out_dev_ptr)))
+
+    def debug_fft(self, in_dev_ptr, n_spectra, hop, out_dev_ptr):
+        return self._chk(self.lib.fosphor_cu_debug_fft(
+            self.h, C.c_void_p(in_dev_ptr), n_spectra, hop, C.c_void_p(out_dev_ptr)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fosphor_cu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

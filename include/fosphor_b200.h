@@ -1,0 +1,161 @@
+/*
+ * fosphor_b200.h - C ABI of libfosphor_b200.so, the B200-native (sm_100a CUDA)
+ * replacement for gr-fosphor's OpenCL compute path.
+ *
+ * Two layers, both plain C (pointers and sizes only, no CUDA/torch types):
+ *
+ *  1. The DROP-IN boundary: the seven fosphor_cl_* entry points of the
+ *     reference's lib/fosphor/cl.h:22-32, same signatures, return codes and
+ *     state machine as lib/fosphor/cl.c:795-1089.  Linking libfosphor against
+ *     this library instead of cl.c + cl_compat.c (+ fft.cl / display.cl) leaves
+ *     fosphor.c, the GL renderer and the GNU Radio sink untouched
+ *     (INTEGRATION.md).  Fixed problem size N=1024 / 128 bins / 1024 rows
+ *     (lib/fosphor/private.h:21-25).
+ *
+ *  2. The parameterised engine fosphor_cu_*: any power-of-two N in
+ *     512..16384, any bin count, device-resident input, in-engine overlap
+ *     (hop addressing), many calls per launch, results as plain device arrays.
+ *
+ * All functions return 0 on success or a negative errno like the reference
+ * (-EINVAL bad size cl.c:881-886, -EIO runtime failure cl.c:842,967,1060,
+ * -ENOMEM cl.c:809, -ENODEV no usable device cl.c:321) unless stated.
+ * There is NO CPU fallback: without a CUDA device init fails with -ENODEV/-EIO.
+ */
+#ifndef FOSPHOR_B200_H
+#define FOSPHOR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------ */
+/* 1. Drop-in boundary (reference: lib/fosphor/cl.h)                         */
+/* ------------------------------------------------------------------------ */
+
+struct fosphor; /* lib/fosphor/private.h:30-55, restated in fosphor_private_abi.h */
+
+/* cl.h:22 / cl.c:799-843.  Allocates the engine into self->cl, leaves
+ * FLG_FOSPHOR_USE_CLGL_SHARING clear so fosphor_init() allocates the host
+ * result images (fosphor.c:50-62).  0, -ENOMEM, -EIO. */
+int fosphor_cl_init(struct fosphor *self);
+
+/* cl.h:23 / cl.c:845-868.  NULL-state safe, sets self->cl = NULL. */
+void fosphor_cl_release(struct fosphor *self);
+
+/* cl.h:25-26 / cl.c:870-968.  samples: host cf32, len complex samples,
+ * len % (16*1024) == 0 and len <= 1024*1024 else -EINVAL.  Asynchronous; the
+ * sample buffer has been fully consumed (staged) when the call returns, so the
+ * caller may recycle it at once (base_sink_c_impl.cc:170-174). */
+int fosphor_cl_process(struct fosphor *self, void *samples, int len);
+
+/* cl.h:27 / cl.c:970-1061.  1: results copied to self->img_waterfall /
+ * img_histogram / buf_spectrum; 0: nothing new; <0 error. */
+int fosphor_cl_finish(struct fosphor *self);
+
+/* cl.h:29 / cl.c:1064-1071.  Pointer retained, read at next process. */
+void fosphor_cl_load_fft_window(struct fosphor *self, float *win);
+
+/* cl.h:30 / cl.c:1073-1079 */
+int fosphor_cl_get_waterfall_position(struct fosphor *self);
+
+/* cl.h:31-32 / cl.c:1081-1089.  Stores scale * 128 and offset. */
+void fosphor_cl_set_histogram_range(struct fosphor *self, float scale, float offset);
+
+/* ------------------------------------------------------------------------ */
+/* 2. Parameterised engine                                                    */
+/* ------------------------------------------------------------------------ */
+
+struct fosphor_cu_params {
+	int fft_len;        /* N: 512, 1024, 2048, 4096, 8192 or 16384 (ref: private.h:21-22) */
+	int n_bins;         /* K power bins, 2..4096              (ref: 128, display.cl:96)    */
+	int wf_rows;        /* W waterfall ring rows, power of two >= batch_max (ref: 1024)   */
+	int batch_mult;     /* spectra per call must be a multiple of this (ref: 16)          */
+	int batch_max;      /* and at most this                              (ref: 1024)      */
+	float histo_t0r;    /* rise time constant   (ref 16.0,   cl.c:714) */
+	float histo_t0d;    /* decay time constant  (ref 1024.0, cl.c:715) */
+	float live_alpha;   /* live IIR alpha       (ref 0.002,  cl.c:716) */
+	float maxhold_keep; /* ref 0.999, display.cl:303 */
+	float maxhold_mix;  /* ref 0.001, display.cl:303 */
+	int device;         /* CUDA device ordinal, -1 = current device */
+};
+
+struct fosphor_cu; /* opaque */
+
+void fosphor_cu_default_params(struct fosphor_cu_params *p);
+int  fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p);
+void fosphor_cu_destroy(struct fosphor_cu *e);
+
+/* Enqueue all subsequent work on this CUDA stream (a cudaStream_t passed as
+ * void*); NULL restores the engine's own non-blocking stream. */
+int fosphor_cu_set_stream(struct fosphor_cu *e, void *cuda_stream);
+
+/* Copies N floats now (cl.c:889-900 uploads lazily; here the copy is taken
+ * at call time, the upload is stream ordered). */
+int fosphor_cu_load_fft_window(struct fosphor_cu *e, const float *win_host);
+/* Stores scale * n_bins and offset (cl.c:1081-1089). */
+int fosphor_cu_set_histogram_range(struct fosphor_cu *e, float scale, float offset);
+
+/* One reference-style call on HOST samples: len complex samples = n_spectra
+ * pre-overlapped windows (cl.c:870-968).  Stages through pinned memory; the
+ * source buffer is free when the call returns. */
+int fosphor_cu_process_host(struct fosphor_cu *e, const void *samples_host, int len);
+
+/* One call on DEVICE-resident samples.  Spectrum s is read at
+ * samples_dev + s*hop complex samples; hop == fft_len is the pre-overlapped
+ * layout, hop = fft_len/overlap does the overlap block's job
+ * (lib/overlap_cc_impl.cc:64-79) without materialising it.  Asynchronous. */
+int fosphor_cu_process_device(struct fosphor_cu *e, const void *samples_dev,
+                              int n_spectra, long long hop);
+
+/* n_calls consecutive calls of `batch` spectra each, results identical to
+ * n_calls fosphor_cu_process_device() calls (the per-call semantics of
+ * display.cl:241-245,303 are kept) but the FFT pass is launched once per
+ * wf_rows spectra.  Asynchronous. */
+int fosphor_cu_process_device_multi(struct fosphor_cu *e, const void *samples_dev,
+                                    int n_calls, int batch, long long hop);
+
+/* HOST raw (not pre-overlapped) stream: n_spectra windows hopping `hop`,
+ * (n_spectra-1)*hop + fft_len complex samples are read.  n_spectra is split
+ * into calls of `batch`.  The copy moves each raw sample once. */
+int fosphor_cu_process_host_raw(struct fosphor_cu *e, const void *raw_host,
+                                int n_calls, int batch, long long hop);
+
+/* cl.c:970-1061 semantics: 1 = results copied into the given host arrays
+ * (any may be NULL): waterfall [wf_rows][N], histogram [n_bins][N],
+ * spectrum float2 live[N] + float2 max[N]; 0 = nothing new. Synchronises. */
+int fosphor_cu_finish(struct fosphor_cu *e, float *waterfall_host,
+                      float *histogram_host, float *spectrum_host);
+/* Wait for all enqueued work (no copies). */
+int fosphor_cu_sync(struct fosphor_cu *e);
+
+int fosphor_cu_get_waterfall_position(const struct fosphor_cu *e);
+
+/* "Plain device arrays" (BASELINE.json north_star): valid until destroy. */
+float *fosphor_cu_device_waterfall(struct fosphor_cu *e);  /* [wf_rows][N]      */
+float *fosphor_cu_device_histogram(struct fosphor_cu *e);  /* [n_bins][N]       */
+float *fosphor_cu_device_spectrum(struct fosphor_cu *e);   /* [2][N][2]         */
+
+/* Write the max-hold trace (N floats, display order) to a device buffer;
+ * input to the multi-GPU ncclMax reduce.  Asynchronous on the engine stream. */
+int fosphor_cu_export_maxhold(struct fosphor_cu *e, float *out_dev);
+
+/* Test hook: windowed forward FFT only, cf32 [n_spectra][N] out (device). */
+int fosphor_cu_debug_fft(struct fosphor_cu *e, const void *samples_dev,
+                         int n_spectra, long long hop, void *out_dev);
+
+/* Per-kernel device timing for the roofline report: when enabled, every FFT and
+ * accumulate launch is bracketed by CUDA events on the engine stream.
+ * profile_read() synchronises, returns the summed kernel durations (ms) and
+ * launch counts since the last read, and resets the counters. */
+int fosphor_cu_profile(struct fosphor_cu *e, int enable);
+int fosphor_cu_profile_read(struct fosphor_cu *e, double *fft_ms, unsigned long long *fft_launches,
+                            double *acc_ms, unsigned long long *acc_launches);
+
+/* Number of kernel launches issued by this engine so far. */
+unsigned long long fosphor_cu_launch_count(const struct fosphor_cu *e);
+const char *fosphor_cu_last_error(const struct fosphor_cu *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

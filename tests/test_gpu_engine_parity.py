@@ -1,0 +1,258 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the CPU oracle.
+Run on the B200 box:  python -m pytest tests -m gpu"""
+import numpy as np
+import pytest
+
+import oracle_lib
+import parity
+import signals
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    return torch
+
+
+def _engine(**kw):
+    from gr_fosphor_b200.engine import Fosphor
+    return Fosphor(**kw)
+
+
+def _to_dev(torch, x):
+    t = torch.from_numpy(np.ascontiguousarray(x).view(np.float32)).cuda()
+    torch.cuda.synchronize()
+    return t
+
+
+# ---------------------------------------------------------------------------
+# stage 1: the transform alone, every supported size
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096, 8192, 16384])
+def test_fft_matches_double_dft(torch_cuda, n):
+    torch = torch_cuda
+    b = 16
+    x = signals.noise_tones(n * b, n_fft=n, seed=100 + n, sigma=0.05)
+    win = oracle_lib.default_window(n)
+    eng = _engine(fft_len=n, n_bins=64, wf_rows=1024, window=win)
+    xin = _to_dev(torch, x)
+    out = torch.empty((b, n, 2), dtype=torch.float32, device="cuda")
+    assert eng.debug_fft(xin.data_ptr(), b, n, out.data_ptr()) == 0
+    eng.sync()
+    got = out.cpu().numpy().view(np.complex64).reshape(b, n)
+    prod = (x.reshape(b, n) * win[None, :]).astype(np.complex64)       # f32 products (fft.cl:416-417)
+    ref = np.fft.fft(prod.astype(np.complex128), axis=1)
+    err = np.abs(got - ref).max(axis=1) / np.abs(ref).max(axis=1)
+    # max_k |X_gpu - X_ref| <= 1e-5 * max_k |X_ref| per spectrum
+    assert err.max() <= 1e-5, err.max()
+    eng.close()
+
+
+def test_fft_hop_addressing(torch_cuda):
+    """hop < N reads overlapping windows from the raw stream (overlap_cc_impl.cc:64-79)."""
+    torch = torch_cuda
+    n, ov, b = 1024, 4, 32
+    raw = signals.noise_tones((b - 1) * (n // ov) + n, seed=5)
+    eng = _engine()
+    out_hop = torch.empty((b, n, 2), dtype=torch.float32, device="cuda")
+    out_mat = torch.empty((b, n, 2), dtype=torch.float32, device="cuda")
+    d_raw = _to_dev(torch, raw)
+    d_mat = _to_dev(torch, signals.overlap_windows(raw, n, ov, b))
+    eng.debug_fft(d_raw.data_ptr(), b, n // ov, out_hop.data_ptr())
+    eng.debug_fft(d_mat.data_ptr(), b, n, out_mat.data_ptr())
+    eng.sync()
+    assert torch.equal(out_hop, out_mat)        # bit exact: same arithmetic, different addressing
+    eng.close()
+
+
+# ---------------------------------------------------------------------------
+# whole path against the oracle
+# ---------------------------------------------------------------------------
+def _run_both(torch, cfg, calls, via="device"):
+    """calls: list of complex64 arrays (one per process call). Returns (engine outputs, oracle)."""
+    eng = _engine(**cfg)
+    okw = dict(fft_len=cfg.get("fft_len", 1024), n_bins=cfg.get("n_bins", 128),
+               wf_rows=cfg.get("wf_rows", 1024), batch_mult=cfg.get("batch_mult", 16),
+               batch_max=cfg.get("batch_max", 1024), t0r=cfg.get("t0r", 16.0),
+               t0d=cfg.get("t0d", 1024.0), alpha=cfg.get("alpha", 0.002))
+    orc = oracle_lib.Oracle(**okw)
+    n = okw["fft_len"]
+    keep = []
+    for x in calls:
+        assert orc.process(x) == 0
+        if via == "device":
+            d = _to_dev(torch, x)
+            keep.append(d)
+            assert eng.process_device(d.data_ptr(), x.size // n) == 0
+        else:
+            assert eng.process(x) == 0
+    rc, host = eng.finish()
+    assert rc == 1 and orc.finish() == 1
+    assert eng.waterfall_position == orc.waterfall_position
+    return eng, host, orc
+
+
+def _written_rows(calls, n, w):
+    total = sum(x.size // n for x in calls)
+    return np.arange(w) if total >= w else np.arange(total)
+
+
+@pytest.mark.parametrize("n_bins", [128, 256])
+@pytest.mark.parametrize("via", ["device", "host"])
+def test_cfg1_burst(torch_cuda, n_bins, via):
+    """BASELINE.json configs[0]: N=1024, one 64k burst (128 bins = reference, 256 = BASELINE)."""
+    x = signals.cfg1_burst()
+    eng, host, orc = _run_both(torch_cuda, dict(n_bins=n_bins), [x], via)
+    parity.check_waterfall(host["waterfall"], orc.waterfall, rows=np.arange(64))
+    # rows never written keep the first-use fill (cl.c:418-436)
+    assert np.array_equal(host["waterfall"][64:], orc.waterfall[64:])
+    parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=64 * 1024)
+    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    eng.close()
+
+
+def test_call_sequence_state(torch_cuda):
+    """state carried across calls of different batch sizes + ring wrap"""
+    n = 1024
+    sizes = (16, 64, 256, 1024, 32, 1024, 48)
+    stream = signals.noise_tones(n * sum(sizes), seed=21)
+    calls, pos = [], 0
+    for b in sizes:
+        calls.append(stream[pos:pos + b * n])
+        pos += b * n
+    eng, host, orc = _run_both(torch_cuda, dict(), calls)
+    parity.check_waterfall(host["waterfall"], orc.waterfall)
+    parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=sum(sizes) * n)
+    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    eng.close()
+
+
+def test_cfg3_persistence_stress(torch_cuda):
+    """BASELINE.json configs[2]: N=4096, 512 bins, overlap 8, fast decay (t0d=20)."""
+    torch = torch_cuda
+    n, k, ov, b = 4096, 512, 8, 256
+    hop = n // ov
+    raw = signals.burst_stress(n_fft=hop, n_spectra=2 * b + ov, seed=3, burst=64)   # bursts every 64 hops
+    cfg = dict(fft_len=n, n_bins=k, wf_rows=1024, t0d=20.0)
+    eng = _engine(**cfg)
+    orc = oracle_lib.Oracle(fft_len=n, n_bins=k, wf_rows=1024, t0d=20.0)
+    d_raw = _to_dev(torch, raw)
+    for c in range(2):
+        off = c * b * hop
+        assert orc.process_hop(raw[off:], b, hop) == 0
+        assert eng.process_device(d_raw.data_ptr() + 8 * off, b, hop) == 0
+    rc, host = eng.finish()
+    orc.finish()
+    parity.check_waterfall(host["waterfall"], orc.waterfall, rows=np.arange(2 * b))
+    parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=2 * b * n)
+    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    eng.close()
+
+
+def test_cfg4_large(torch_cuda):
+    """BASELINE.json configs[3] shape on one GPU: N=16384, 1024 bins, B=1024 (one channel)."""
+    n, k, b = 16384, 1024, 1024
+    x = signals.noise_tones(n * b, n_fft=n, seed=10, sigma=0.02)
+    eng, host, orc = _run_both(torch_cuda, dict(fft_len=n, n_bins=k, wf_rows=1024), [x])
+    parity.check_waterfall(host["waterfall"], orc.waterfall)
+    parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=b * n)
+    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    eng.close()
+
+
+@pytest.mark.parametrize("n", [512, 2048, 8192])
+def test_sweep_sizes(torch_cuda, n):
+    """BASELINE.json configs[4] sizes not covered above, 256 bins."""
+    b = 64
+    x = signals.noise_tones(n * b, n_fft=n, seed=50 + n, sigma=0.02)
+    eng, host, orc = _run_both(torch_cuda, dict(fft_len=n, n_bins=256, wf_rows=1024), [x])
+    parity.check_waterfall(host["waterfall"], orc.waterfall, rows=np.arange(b))
+    parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=b * n)
+    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    eng.close()
+
+
+def test_dc_contention_and_zeros(torch_cuda):
+    """worst-case atomic contention (constant input: one bin per column) and the -inf path."""
+    n, b = 1024, 256
+    dc = np.full(n * b, 0.25 + 0.1j, np.complex64)
+    eng, host, orc = _run_both(torch_cuda, dict(), [dc])
+    parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=b * n)
+    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    eng.close()
+
+    zeros = np.zeros(n * 16, np.complex64)
+    data = signals.noise_tones(n * 32, seed=11)
+    eng, host, orc = _run_both(torch_cuda, dict(), [zeros, data])
+    wf = host["waterfall"]
+    assert np.all(np.isneginf(wf[:16])) and np.all(np.isneginf(orc.waterfall[:16]))
+    parity.check_waterfall(wf, orc.waterfall, rows=np.arange(16, 48))
+    parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=48 * n)
+    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    eng.close()
+
+
+def test_validation_and_state_machine(torch_cuda):
+    """cl.c:881-886 / :970-994 return codes"""
+    eng = _engine()
+    rc, host = eng.finish()                 # BOOTING: clears, returns 1
+    assert rc == 1
+    scale, offset = oracle_lib.power_range(1024, 0, 10)
+    assert np.all(host["waterfall"] == -offset) and np.all(host["spectrum"] == -offset)
+    assert np.all(host["histogram"] == 0)
+    assert eng.finish()[0] == 0             # READY: nothing new
+    assert eng.process(np.zeros(1024 * 15, np.complex64)) == -22
+    assert eng.process(np.zeros(1024 * 1040, np.complex64)) == -22
+    assert eng.finish()[0] == 0
+    assert eng.process(signals.noise_tones(1024 * 16, seed=1)) == 0
+    assert eng.waterfall_position == 16
+    assert eng.finish()[0] == 1
+    eng.close()
+
+
+# ---------------------------------------------------------------------------
+# size-independent properties at full size
+# ---------------------------------------------------------------------------
+def test_multi_call_launch_equals_single_calls(torch_cuda):
+    """process_device_multi == the same calls one by one, bit for bit (cfg2 shape)."""
+    torch = torch_cuda
+    n, k, ov, b, calls = 1024, 256, 4, 1024, 6
+    hop = n // ov
+    raw = signals.noise_tones((calls * b - 1) * hop + n, seed=2)
+    d_raw = _to_dev(torch, raw)
+    a = _engine(n_bins=k, wf_rows=4096)
+    c = _engine(n_bins=k, wf_rows=4096)
+    assert a.process_device_multi(d_raw.data_ptr(), calls, b, hop) == 0
+    for i in range(calls):
+        assert c.process_device(d_raw.data_ptr() + 8 * i * b * hop, b, hop) == 0
+    _, ha = a.finish()
+    _, hc = c.finish()
+    for key in ("waterfall", "histogram", "spectrum"):
+        assert np.array_equal(ha[key], hc[key]), key
+    assert a.waterfall_position == c.waterfall_position == (calls * b) % 4096
+    # and host-fed raw stream == device path
+    h = _engine(n_bins=k, wf_rows=4096)
+    assert h.process_host_raw(raw, calls, b, hop) == 0
+    _, hh = h.finish()
+    for key in ("waterfall", "histogram", "spectrum"):
+        assert np.array_equal(ha[key], hh[key]), key
+    for e in (a, c, h):
+        e.close()
+
+
+def test_histogram_mass_property(torch_cuda):
+    """From a zero histogram one call deposits, per column, exactly the mass the
+    closed form predicts from hit counts summing to B: sum_bins d(hc)*(1-e(hc)).
+    Checked against the oracle's hit counts at the full cfg2 batch size."""
+    n, k, b = 1024, 256, 1024
+    x = signals.noise_tones(n * b, seed=33)
+    eng, host, orc = _run_both(torch_cuda, dict(n_bins=k), [x])
+    hits = orc.last_hits
+    assert np.all(hits.sum(axis=0) == b)
+    parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=b * n)
+    # live IIR linearity in the carry: second identical call moves live towards the same mean
+    eng.close()
