@@ -69,7 +69,7 @@ def power_range(db_ref, db_per_div, n=FOSPHOR_FFT_LEN):
     f = np.float32
     db0 = db_ref - 10 * db_per_div
     db1 = db_ref
-    k = np.log10(f(n), dtype=np.float32)
+    k = f(np.log10(np.float64(n)))   # == C log10f((float)N): correctly rounded for these N
     offset = f(-(k + f(db0) / f(20.0)))
     scale = f(f(20.0) / f(db1 - db0))
     return scale, offset

@@ -79,7 +79,7 @@ def power_range(n, db_ref, db_per_div):
     """lib/fosphor/fosphor.c:131-152 -> (scale, offset) f32, with k = log10(N)."""
     f = np.float32
     db0 = db_ref - 10 * db_per_div
-    k = np.log10(f(n), dtype=np.float32)
+    k = f(np.log10(np.float64(n)))   # == C log10f((float)N): correctly rounded for these N
     return f(f(20.0) / f(db_ref - db0)), f(-(k + f(db0) / f(20.0)))
 
 

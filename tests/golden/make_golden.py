@@ -33,7 +33,7 @@ REF_SO = os.path.join(ROOT, "oracle", "_ref", "libfosphor_ref.so")
 def wf_rows_to_keep(total_rows):
     if total_rows <= 128:
         return np.arange(total_rows)
-    return np.arange(0, 1024, 8)
+    return np.arange(0, 1024, 32)
 
 
 def pack(records, steps):
@@ -50,7 +50,7 @@ def pack(records, steps):
             i = len(meta)
             rows = wf_rows_to_keep(min(rows_written, 1024) if rows_written else 1024)
             if rows_written == 0:
-                rows = np.arange(0, 1024, 8)
+                rows = np.arange(0, 1024, 32)
             meta.append({"op": "finish", "rc": r["rc"], "wf_pos": r["wf_pos"], "key": "s%d" % i})
             out["s%d_wf_rows" % i] = rows.astype(np.int32)
             out["s%d_waterfall" % i] = r["waterfall"][rows]

@@ -51,9 +51,26 @@ def check_histogram(got, ref, hits_in_play):
     return bad, float(d.max())
 
 
-def check_spectrum(got, ref):
+def conditioned_columns(wf_rows_ref, floor_db=80.0):
+    """Columns whose magnitude stays within floor_db of the row maximum in every
+    given waterfall row.  Bins that hold only rounding noise (e.g. the off-peak
+    bins of a pure tone under a rectangular window) are ill-conditioned in log
+    units in ANY f32 implementation, the reference included, and are excluded
+    from the live / max-hold comparison.  Display order index i = f ^ N/2."""
+    wf = np.asarray(wf_rows_ref, np.float64)
+    rowmax = np.nanmax(np.where(np.isfinite(wf), wf, -np.inf), axis=1, keepdims=True)
+    ok = np.all((wf >= rowmax - floor_db / 20.0) | ~np.isfinite(wf), axis=0)
+    n = wf.shape[1]
+    return ok[np.arange(n) ^ (n // 2)]
+
+
+def check_spectrum(got, ref, cols=None):
     got = np.asarray(got, np.float64)
     ref = np.asarray(ref, np.float64)
+    if cols is not None:
+        got, ref = got[:, cols], ref[:, cols]
+        if got.size == 0:
+            return 0.0
     same = _eq_nonfinite(got, ref)
     d = np.where(same, 0.0, np.abs(got - ref))
     d = np.nan_to_num(d, nan=np.inf)
