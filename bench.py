@@ -5,9 +5,10 @@
   python bench.py --impl reference --gpus N --steps K ...  (the reference's own path)
 
 Workload = BASELINE.json configs[1]: N=1024 FFT, 256 power bins, overlap 4,
-continuous synthetic IQ, calls of B=1024 spectra.  One STEP is one display
-frame of the reference sink: 8 process calls (base_sink_c_impl.cc:133-146) =
-8192 spectra = 8.39 Mcomplex-samples entering the FFT.  The stream is the
+continuous 100 Msps synthetic IQ, calls of B=1024 spectra.  One STEP is one
+second of that signal: 1e8 raw samples -> 4e8 samples entering
+the FFT = 384 calls of 1024 spectra (393,216 spectra, 402.7 Msamples), so
+1000 / ms_per_step is the real-time headroom.  The stream is the
 pre-overlapped one the reference's fosphor_cl_process() receives (overlap_cc
 upstream, lib/overlap_cc_impl.cc:64-79); the in-engine-overlap variant (raw
 stream, hop = N/4) is reported next to it under "overlap_in_engine".
@@ -35,8 +36,9 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-N_FFT, N_BINS, OVERLAP, BATCH, CALLS_PER_STEP = 1024, 256, 4, 1024, 8
-WF_ROWS = 8192   # device ring holds one whole step so the FFT pass is one launch per step
+N_FFT, N_BINS, OVERLAP, BATCH, CALLS_PER_STEP = 1024, 256, 4, 1024, 384
+WF_ROWS = 8192   # device ring: the FFT pass is launched once per 8 calls (8192 spectra)
+REF_CALLS_PER_STEP = 8   # reference arm: one sink frame (base_sink_c_impl.cc:133-146) per step
 
 
 def algorithmic_bytes_per_call(n, k, b, r):
@@ -58,52 +60,54 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region"""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled through NVML every ~5 ms during the timed region."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self.thr = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=self._pump, daemon=True)
-            self.thr.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except ValueError:
+                    idx = self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown,
+                     "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown,
+                     "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            def pump():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for k, bit in names.items():
+                            if r & bit:
+                                self.reasons.add(k)
+                    except Exception:
+                        pass
+                    time.sleep(0.004)
+            self.thr = threading.Thread(target=pump, daemon=True)
+            self.thr.start()
+        except Exception as exc:
+            self.reasons.add("nvml unavailable: %s" % exc)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
-                continue
-            for nme, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self.thr:
+            self.thr.join(timeout=2)
+        sm = self.samples
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def synth_stream_torch(torch, n_samples, seed, device):
@@ -112,12 +116,14 @@ def synth_stream_torch(torch, n_samples, seed, device):
     g.manual_seed(seed)
     x = torch.randn((n_samples, 2), generator=g, device=device, dtype=torch.float32) * (0.01 / np.sqrt(2.0))
     rng = np.random.default_rng(seed)
-    t = torch.arange(n_samples, device=device, dtype=torch.float32)
+    t = torch.arange(n_samples, device=device, dtype=torch.float64)
     for f, a, p in zip(rng.uniform(-0.5, 0.5, 8), np.exp(rng.uniform(np.log(0.02), np.log(0.6), 8)),
                        rng.uniform(0, 2 * np.pi, 8)):
-        ph = (t * float(f)) % 1.0 * (2 * np.pi) + float(p)
+        ph = (torch.remainder(t * float(f), 1.0) * (2 * np.pi) + float(p)).to(torch.float32)
         x[:, 0] += float(a) * torch.cos(ph)
         x[:, 1] += float(a) * torch.sin(ph)
+        del ph
+    del t
     return x
 
 
@@ -134,7 +140,7 @@ def cpu_baseline_port(seconds_budget=12.0):
         orc.process(x)
         calls += 1
         el = time.perf_counter() - t0
-        if (calls >= CALLS_PER_STEP and el > seconds_budget) or calls >= 64 * CALLS_PER_STEP:
+        if (calls >= 8 and el > seconds_budget) or calls >= 4096:
             break
     orc.finish()
     msps = calls * BATCH * N_FFT / el / 1e6
@@ -166,7 +172,9 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the engine enqueues on it and torch.cuda.Event times it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     peak, peak_src = measured_peaks()
 
     n, k, b, calls = N_FFT, N_BINS, BATCH, CALLS_PER_STEP
@@ -176,14 +184,12 @@ def run_b200(args):
 
     eng = Fosphor(fft_len=n, n_bins=k, wf_rows=WF_ROWS, device=local, stream=stream.cuda_stream)
 
-    # ---- inputs: pre-overlapped pool (> L2) and a raw stream for the hop mode ----
-    pool_n = 6                                       # 6 x 64 MiB = 384 MiB > 126 MB L2
+    # ---- inputs: two distinct seconds of signal, raw and pre-overlapped (3.2 GB each >> L2) ----
+    pool_n = raw_pool_n = 2
     raw_len = (spectra_per_step - 1) * hop + n
-    raw_pool_n = 10                                  # 10 x 16 MiB = 168 MB of distinct raw data
     raws = [synth_stream_torch(torch, raw_len, 1000 * rank + 2 + i, dev) for i in range(raw_pool_n)]
-    idx = (torch.arange(spectra_per_step, device=dev)[:, None] * hop + torch.arange(n, device=dev)[None, :]).reshape(-1)
-    pool = [raws[i][idx].contiguous() for i in range(pool_n)]     # what overlap_cc would emit
-    del idx
+    # what overlap_cc would emit: [spectra][N] windows hopping N/4
+    pool = [r.unfold(0, n, hop).permute(0, 2, 1).contiguous().view(-1, 2) for r in raws]
     maxhold = torch.empty(n, dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
 
@@ -232,12 +238,15 @@ def run_b200(args):
 
     # per-kernel durations: same loop again with event pairs around each launch
     eng.profile(True)
-    timed(lambda i: step_device(i, True), args.steps, 1)
+    prof_steps = min(args.steps, 5)
+    timed(lambda i: step_device(i, True), prof_steps, 0)
     prof = eng.profile_read()
     eng.profile(False)
     fft_ms = prof["fft_ms"] / max(1, prof["fft_launches"])
-    acc_ms = prof["acc_ms"] / max(1, prof["acc_launches"])
-    fft_bytes = fft_kernel_bytes(n, spectra_per_step, 1.0)
+    count_ms = prof["count_ms"] / max(1, prof["count_launches"])
+    update_ms = prof["update_ms"] / max(1, prof["update_launches"])
+    spectra_per_fft_launch = spectra_per_step * prof_steps // max(1, prof["fft_launches"])
+    fft_bytes = fft_kernel_bytes(n, spectra_per_fft_launch, 1.0)
     achieved = fft_bytes / (fft_ms * 1e-3) / 1e9
     step_bytes = calls * algorithmic_bytes_per_call(n, k, b, 1.0)
 
@@ -252,32 +261,35 @@ def run_b200(args):
     value_hop = world * args.steps * samples_per_step / (ms_hop * 1e-3) / 1e6
 
     # ---- e2e through the C ABI with host buffers ----
-    h_pool = [torch.empty((samples_per_step, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
-    for hp, src in zip(h_pool, pool):
-        hp.copy_(src)
-    h_raw = [torch.empty((raw_len, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
-    for hp, src in zip(h_raw, raws):
-        hp.copy_(src)
+    h_pool = [torch.empty((samples_per_step, 2), dtype=torch.float32).pin_memory()]
+    h_pool[0].copy_(pool[0])
+    h_raw = [torch.empty((raw_len, 2), dtype=torch.float32).pin_memory()]
+    h_raw[0].copy_(raws[0])
     torch.cuda.synchronize()
     call_len = b * n
+    r_wf = torch.empty((1024, n), dtype=torch.float32).pin_memory()
+    r_hist = torch.empty((k, n), dtype=torch.float32).pin_memory()
+    r_spec = torch.empty((2, n, 2), dtype=torch.float32).pin_memory()
+
+    def finish_e2e():
+        rc = eng.finish_into(r_wf.data_ptr(), r_hist.data_ptr(), r_spec.data_ptr())
+        assert rc == 1
 
     def step_e2e(i):
-        base = h_pool[i % 2].data_ptr()
+        base = h_pool[0].data_ptr()
         for c in range(calls):
             eng.process_host_ptr(base + 8 * c * call_len, call_len)
         if dist is not None:
             eng.export_maxhold(maxhold.data_ptr())
             dist.all_reduce(maxhold, op=dist.ReduceOp.MAX)
-        rc, _ = eng.finish()
-        assert rc == 1
+        finish_e2e()
 
     def step_e2e_raw(i):
-        eng.process_host_raw_ptr(h_raw[i % 2].data_ptr(), calls, b, hop)
+        eng.process_host_raw_ptr(h_raw[0].data_ptr(), calls, b, hop)
         if dist is not None:
             eng.export_maxhold(maxhold.data_ptr())
             dist.all_reduce(maxhold, op=dist.ReduceOp.MAX)
-        rc, _ = eng.finish()
-        assert rc == 1
+        finish_e2e()
 
     def timed_host(fn, steps, warmup):
         for i in range(warmup):
@@ -296,12 +308,14 @@ def run_b200(args):
             el = float(t.item())
         return el
 
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(2, min(args.steps, 4))
+    del pool, raws
+    torch.cuda.empty_cache()
     eng_dev = eng
     eng = Fosphor(fft_len=n, n_bins=k, wf_rows=1024, device=local, stream=stream.cuda_stream)   # reference-sized ring
-    ms_e2e = timed_host(step_e2e, e2e_steps, 3)
+    ms_e2e = timed_host(step_e2e, e2e_steps, 1)
     e2e = world * e2e_steps * samples_per_step / (ms_e2e * 1e-3) / 1e6
-    ms_e2e_raw = timed_host(step_e2e_raw, e2e_steps, 3)
+    ms_e2e_raw = timed_host(step_e2e_raw, e2e_steps, 1)
     e2e_raw = world * e2e_steps * samples_per_step / (ms_e2e_raw * 1e-3) / 1e6
     d2h = 4 * (1024 * n + k * n + 4 * n)
     eng.close()
@@ -317,11 +331,12 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: N=1024, 256 bins, overlap=4 (pre-overlapped stream, r=1), "
-                                   "B=1024 spectra/call, step = 8 calls = 8192 spectra",
+            "realtime_factor_100Msps": 1000.0 / (ms / args.steps),
+            "config": {"workload": "cfg2: N=1024, 256 bins, overlap=4 (pre-overlapped stream, r=1), B=1024 "
+                                   "spectra/call, step = 1 s of 100 Msps IQ = 384 calls = 393216 spectra",
                        "fft_len": n, "n_bins": k, "overlap": OVERLAP, "batch": b, "calls_per_step": calls,
                        "wf_rows": WF_ROWS,
-                       "l2": "inputs rotate over a %d MiB pool (> 126 MB L2)" % (pool_n * samples_per_step * 8 // 2**20),
+                       "l2": "each step streams a %d MiB input (two alternating buffers), far larger than the 126 MB L2" % (samples_per_step * 8 // 2**20),
                        "multi_gpu": "one channel per GPU, NCCL max all-reduce of max-hold per step" if world > 1 else "single"},
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
@@ -329,12 +344,13 @@ def run_b200(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic,
                          "bytes_per_launch": fft_bytes, "ms_per_launch": fft_ms,
-                         "accumulate_ms_per_launch": acc_ms,
+                         "spectra_per_launch": spectra_per_fft_launch,
+                         "count_ms_per_launch": count_ms, "update_ms_per_launch": update_ms,
                          "step_algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                          "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e, "unit": "Mcomplex-samples/s",
                     "h2d_bytes_per_step": 8 * samples_per_step, "d2h_bytes_per_step": d2h,
-                    "api": "fosphor_cu_process_host x8 + fosphor_cu_finish (host pre-overlapped stream)"},
+                    "api": "fosphor_cu_process_host x384 + fosphor_cu_finish (page-locked host pre-overlapped stream)"},
             "overlap_in_engine": {"value": value_hop, "e2e": e2e_raw, "unit": "Mcomplex-samples/s",
                                   "h2d_bytes_per_step": 8 * raw_len,
                                   "note": "raw stream, hop=N/4 addressing inside the FFT kernel (r=1/4)"},
@@ -359,7 +375,7 @@ def run_reference(args):
     if rank != 0:
         return
     import signals
-    n, b, calls = N_FFT, BATCH, CALLS_PER_STEP
+    n, b, calls = N_FFT, BATCH, REF_CALLS_PER_STEP
     raw = signals.noise_tones((calls * b - 1) * (n // OVERLAP) + n, seed=2)
     x = signals.overlap_windows(raw, n, OVERLAP, calls * b).reshape(calls, b * n)
     samples_per_step = calls * b * n
@@ -409,7 +425,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -1,26 +1,37 @@
 /*
- * accumulate.cuh - kernel 2 of the hot path: per frequency column, fold the B
- * log-power rows of one call into the persistence state.
+ * accumulate.cuh - kernels 2a/2b of the hot path: fold the log-power rows of
+ * one or more calls into the persistence state.
  *
  * Replaces the second half of the reference's display program:
  *   lib/fosphor/display.cl:149-150,186-214  live spectrum (weighted IIR)
  *   lib/fosphor/display.cl:160-178          bin mapping + hit counting
  *   lib/fosphor/display.cl:217-254          histogram rise / decay
  *   lib/fosphor/display.cl:257-310          max hold with decay
- * The reference runs this on a fixed 64 work-groups that each loop over the
- * whole batch (cl.c:945-948).  Here the batch is split over S CTAs per tile of
- * 32 columns: every CTA counts its rows into a shared-memory tile
- * hits[bin][lane] (lane == column, so a warp never has a bank conflict; the
- * 8 warps of the CTA meet only through shared atomics), flushes the non-zero
- * counts once to a global u32 array, and the LAST CTA of a tile to finish
- * (ticket counter) applies the rise/decay, live and max-hold updates.  With
- * S == 1 the global hit array is bypassed.
+ * The reference runs all of this on a fixed 64 work-groups that each loop over
+ * the whole batch and then over all bins (cl.c:945-948).  Here the work is cut
+ * along its real dependencies:
+ *
+ *  count_kernel  (embarrassingly parallel over tiles x slices)
+ *      A slice is a run of rows of ONE call; a tile is 32 columns.  Each CTA
+ *      counts its rows into a shared-memory tile hits[bin][lane] (lane ==
+ *      column: a warp never has a bank conflict, the 8 warps of the CTA meet
+ *      only through shared atomics), then stores the whole tile once, as u16,
+ *      to cnt[slice][bin][col], plus the slice's partial live sum and maximum
+ *      per column.  Nothing is read-modify-written in global memory, so there
+ *      is nothing to clear between calls.
+ *
+ *  update_kernel (parallel over the K x N state cells and the N columns)
+ *      The only sequential dependence of the whole path is along the CALL axis
+ *      inside one cell:  hv <- (hv - d) e + d  with (d, e) a function of that
+ *      call's hit count.  One thread owns one cell (or one column for
+ *      live / max-hold), sums the slices of each call and walks the calls in
+ *      order.  Many calls are therefore folded by ONE launch with exactly the
+ *      per-call semantics of display.cl:241-247,303.
  *
  * The rise/decay closed form depends only on (hit count, B):
  *   a = hc/B; b = a/t0r; c = b + 1/t0d; d = b/c; e = (1-c)^B; hv' = (hv-d)e+d
  * so the host tabulates (d, e) for hc = 0..B and the live weights
- * (1-alpha)^(B-1-s) once per distinct B (engine.cu: BatchTables); the kernel
- * does a table lookup + FMA per state cell instead of two transcendental calls.
+ * (1-alpha)^(B-1-s) once per distinct B (engine.cu: BatchTables).
  */
 #pragma once
 #include <cfloat>
@@ -31,162 +42,205 @@ namespace fosphor_b200 {
 constexpr int ACC_COLS = 32;     /* columns per tile == warp width */
 constexpr int ACC_WARPS = 8;
 constexpr int ACC_THREADS = ACC_WARPS * 32;
+constexpr int UPD_THREADS = 256;
+constexpr int UPD_GROUP = 8;     /* calls whose loads are issued together */
 constexpr int REF_ROWS = 16;     /* display.cl:206-207 "sum / get_local_size(1)" */
 
 struct AccumArgs {
-	const float *wf;        /* waterfall ring [W][N] (kernel 1 output)       */
-	float *hist;            /* histogram state [K][N]                        */
-	float2 *spectrum;       /* live[N] then max[N], display order            */
-	unsigned *ghits;        /* [K][N] cross-CTA hit counts (zero between calls) */
-	float *part_live;       /* [S][N] per-split partial live sums            */
-	float *part_max;        /* [S][N] per-split partial maxima               */
-	unsigned *tickets;      /* [N/32] arrival counters (zero between calls)  */
-	const float *weights;   /* [B]   (1-alpha)^(B-1-s)                       */
-	const float2 *lut;      /* [B+1] (d, e) per hit count                    */
-	int n, n_bins, wf_mask, wf_pos;
-	int batch, splits, rows_per_split;
-	float hscale, hofs;     /* cl.c:1087-1088 */
-	float alpha, live_carry;/* live_carry = (1-alpha)^B, display.cl:210      */
-	float mh_keep, mh_mix;  /* display.cl:303 */
+	const float *wf;          /* waterfall ring [W][N] (kernel 1 output)        */
+	float *hist;              /* histogram state [K][N]                         */
+	float2 *spectrum;         /* live[N] then max[N], display order             */
+	unsigned short *cnt;      /* [slices][K][N] hit counts of this chunk        */
+	float *part_live;         /* [calls][row blocks per call][N] partial live sums */
+	float *part_max;          /* [calls][row blocks per call][N] partial maxima    */
+	const float *weights;     /* [B]   (1-alpha)^(B-1-s)                        */
+	const float2 *lut;        /* [B+1] (d, e) per hit count                     */
+	int n, n_bins, wf_mask, wf_pos;   /* wf_pos: ring row of the chunk's first spectrum */
+	int batch;                /* B, spectra per call                            */
+	int n_calls;              /* calls in this chunk                            */
+	int splits;               /* slices per call                                */
+	int rows_per_split;
+	float hscale, hofs;       /* cl.c:1087-1088 */
+	float alpha, live_carry;  /* live_carry = (1-alpha)^B, display.cl:210       */
+	float mh_keep, mh_mix;    /* display.cl:303 */
 };
 
-__device__ __forceinline__ int map_bin(float x, int kmax)
+__device__ __forceinline__ int map_bin(float x, float kmaxf)
 {
-	/* display.cl:161-165: (int)round(x) half away from zero, clamped to
-	 * [0, K-1].  NaN and -inf -> 0, +inf -> K-1 (what the reference yields on
-	 * the NVIDIA OpenCL runtime; fixed as the rule in DESIGN.md). */
-	if (!(x > 0.0f))
-		return 0;
-	if (x >= (float)kmax)
-		return kmax;
-	const float fl = floorf(x);
-	return (int)fl + ((x - fl) >= 0.5f ? 1 : 0);   /* <= kmax since x < kmax */
+	/* display.cl:161-165: (int)round(x), half away from zero, clamped to
+	 * [0, K-1].  Clamping first is equivalent and makes the special values
+	 * explicit: NaN and -inf -> 0 (fmaxf drops the NaN), +inf -> K-1 - what the
+	 * reference yields on the NVIDIA OpenCL runtime; the rule is fixed in
+	 * DESIGN.md.  For x >= 0, round-half-away = rint(x) bumped on exact ties. */
+	x = fminf(fmaxf(x, 0.0f), kmaxf);
+	float r = rintf(x);
+	if (x - r == 0.5f)
+		r += 1.0f;
+	return (int)r;
 }
 
+constexpr int CNT_INFLIGHT = 8;   /* rows whose loads a warp issues before consuming any */
+constexpr int ROWBLOCK = 128;     /* canonical unit of the f32 live partial sums */
+constexpr int BLK_GROUP = 8;      /* row blocks reduced per pass through shared memory */
+
+/* The f32 live-spectrum partial sums are formed per ROWBLOCK rows in a fixed
+ * order (warp w takes rows w, w+8, ... of the block; the 8 warp partials are
+ * added in warp order; update_kernel adds the blocks in row order), so the
+ * result does not depend on how a call is cut into slices. */
 __global__ void __launch_bounds__(ACC_THREADS)
-accumulate_kernel(const AccumArgs a)
+count_kernel(const AccumArgs a)
 {
 	extern __shared__ unsigned sh_hits[];           /* [K][32] */
-	__shared__ float sh_live[ACC_WARPS][32];
-	__shared__ float sh_max[ACC_WARPS][32];
-	__shared__ unsigned sh_ticket;
+	__shared__ float sh_live[BLK_GROUP][ACC_WARPS][32];
+	__shared__ float sh_max[BLK_GROUP][ACC_WARPS][32];
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int tile = blockIdx.x, split = blockIdx.y;
+	const int tile = blockIdx.x, slice = blockIdx.y;
+	const int call = slice / a.splits, split = slice - call * a.splits;
 	const int col = tile * ACC_COLS + lane;
 	const int K = a.n_bins, N = a.n;
 
-	for (int i = threadIdx.x; i < K * 32; i += ACC_THREADS)
-		sh_hits[i] = 0;
+	{
+		uint4 *z = reinterpret_cast<uint4 *>(sh_hits);
+		for (int i = threadIdx.x; i < K * 8; i += ACC_THREADS)
+			z[i] = make_uint4(0u, 0u, 0u, 0u);
+	}
 	__syncthreads();
 
-	/* ---- count: rows [row0, row1) of this call ---- */
+	/* rows [row0, row1) of this call; rows_per_split is a multiple of ROWBLOCK */
 	const int row0 = split * a.rows_per_split;
 	const int row1 = min(a.batch, row0 + a.rows_per_split);
-	float live = 0.0f, mx = -1000.0f;               /* display.cl:91,113 */
-	const int kmax = K - 1;
+	const unsigned ring0 = (unsigned)(a.wf_pos + call * a.batch);
+	const unsigned mask = (unsigned)a.wf_mask;
+	const float *base = a.wf + col;
+	const float kmaxf = (float)(K - 1);
+	unsigned *my_hits = sh_hits + lane;
+	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
+	const size_t part_base = (size_t)call * blocks_per_call;
 
-#pragma unroll 4
-	for (int s = row0 + warp; s < row1; s += ACC_WARPS) {
-		const float pwr = __ldcg(&a.wf[(size_t)((a.wf_pos + s) & a.wf_mask) * N + col]);
-		live = fmaf(pwr, __ldg(&a.weights[s]), live);       /* :149-150 */
-		mx = fmaxf(mx, pwr);                                /* :139 */
-		const int bin = map_bin(__fmul_rn(a.hscale, __fadd_rn(pwr, a.hofs)), kmax);
-		atomicAdd(&sh_hits[bin * 32 + lane], 1u);           /* :170-177 */
-	}
-	sh_live[warp][lane] = live;
-	sh_max[warp][lane] = mx;
-	__syncthreads();
-
-	if (warp == 0) {
-		float sum = 0.0f, m = -1000.0f;
+	for (int g0 = row0; g0 < row1; g0 += ROWBLOCK * BLK_GROUP) {
+		const int g1 = min(row1, g0 + ROWBLOCK * BLK_GROUP);
+		int nblk = 0;
+		for (int b0 = g0; b0 < g1; b0 += ROWBLOCK, nblk++) {
+			const int b1 = min(g1, b0 + ROWBLOCK);
+			float live = 0.0f, mx = -1000.0f;       /* display.cl:91,113 */
+			for (int s0 = b0 + warp; s0 < b1; s0 += ACC_WARPS * CNT_INFLIGHT) {
+				float pw[CNT_INFLIGHT], wt[CNT_INFLIGHT];
 #pragma unroll
-		for (int w = 0; w < ACC_WARPS; w++) {
-			sum += sh_live[w][lane];
-			m = fmaxf(m, sh_max[w][lane]);
-		}
-		sh_live[0][lane] = sum;
-		sh_max[0][lane] = m;
-		if (a.splits > 1) {
-			a.part_live[(size_t)split * N + col] = sum;
-			a.part_max[(size_t)split * N + col] = m;
-		}
-	}
-
-	bool last = true;
-	if (a.splits > 1) {
-		/* flush non-zero counts once, then take a ticket */
-		for (int bin = warp; bin < K; bin += ACC_WARPS) {
-			const unsigned c = sh_hits[bin * 32 + lane];
-			if (c)
-				atomicAdd(&a.ghits[(size_t)bin * N + col], c);
-		}
-		__threadfence();
-		__syncthreads();
-		if (threadIdx.x == 0)
-			sh_ticket = atomicAdd(&a.tickets[tile], 1u);
-		__syncthreads();
-		last = (sh_ticket == (unsigned)(a.splits - 1));
-		if (!last)
-			return;
-		__threadfence();
-		if (threadIdx.x == 0)
-			a.tickets[tile] = 0;                /* ready for the next call */
-	} else {
-		__syncthreads();
-	}
-
-	/* ---- update (one CTA per tile gets here) ---- */
-	for (int bin = warp; bin < K; bin += ACC_WARPS) {
-		const size_t idx = (size_t)bin * N + col;
-		unsigned hc;
-		if (a.splits > 1) {
-			hc = __ldcg(&a.ghits[idx]);
-			if (hc)
-				a.ghits[idx] = 0;
-		} else {
-			hc = sh_hits[bin * 32 + lane];
-		}
-		float hv = a.hist[idx];
-		if (hv <= 0.01f && hc == 0)                     /* display.cl:237-238 */
-			continue;
-		const float2 de = __ldg(&a.lut[hc]);
-		hv = __fadd_rn(__fmul_rn(__fsub_rn(hv, de.x), de.y), de.x);   /* :247 */
-		hv = fminf(fmaxf(hv, 0.0f), 1.0f);                            /* :250 */
-		a.hist[idx] = hv;
-	}
-
-	if (warp == 0) {
-		float sum, bmax;
-		if (a.splits > 1) {
-			sum = 0.0f;
-			bmax = -1000.0f;
-			for (int sp = 0; sp < a.splits; sp++) {
-				sum += __ldcg(&a.part_live[(size_t)sp * N + col]);
-				bmax = fmaxf(bmax, __ldcg(&a.part_max[(size_t)sp * N + col]));
+				for (int u = 0; u < CNT_INFLIGHT; u++) {
+					const int s = s0 + u * ACC_WARPS;
+					if (s < b1) {
+						pw[u] = __ldcg(base + (size_t)(((ring0 + (unsigned)s) & mask) * (unsigned)N));
+						wt[u] = __ldg(&a.weights[s]);
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < CNT_INFLIGHT; u++) {
+					if (s0 + u * ACC_WARPS < b1) {
+						live = fmaf(pw[u], wt[u], live);                  /* :149-150 */
+						mx = fmaxf(mx, pw[u]);                            /* :139 */
+						const int bin = map_bin(__fmul_rn(a.hscale, __fadd_rn(pw[u], a.hofs)), kmaxf);
+						atomicAdd(my_hits + bin * 32, 1u);                /* :170-177 */
+					}
+				}
 			}
-		} else {
-			sum = sh_live[0][lane];
-			bmax = sh_max[0][lane];
+			sh_live[nblk][warp][lane] = live;
+			sh_max[nblk][warp][lane] = mx;
 		}
+		__syncthreads();
+		if (warp < nblk) {
+			float sum = 0.0f, m = -1000.0f;
+#pragma unroll
+			for (int w = 0; w < ACC_WARPS; w++) {
+				sum += sh_live[warp][w][lane];
+				m = fmaxf(m, sh_max[warp][w][lane]);
+			}
+			const size_t o = (part_base + (size_t)(g0 / ROWBLOCK + warp)) * N + col;
+			a.part_live[o] = sum;
+			a.part_max[o] = m;
+		}
+		__syncthreads();
+	}
 
-		const int half = N >> 1;
-		const int i = col ^ half;                                 /* display.cl:201 */
-		const float xpos = ((float)i / (float)half) - 1.0f;       /* :209 */
+	unsigned short *dst = a.cnt + (size_t)slice * K * N + col;
+#pragma unroll 4
+	for (int bin = warp; bin < K; bin += ACC_WARPS)
+		dst[(size_t)bin * N] = (unsigned short)sh_hits[bin * 32 + lane];
+}
 
+/* blocks [0, cell_blocks): one thread per histogram cell (bin-major, so a warp
+ * touches 32 consecutive columns of one bin); blocks beyond: one thread per column. */
+__global__ void __launch_bounds__(UPD_THREADS)
+update_kernel(const AccumArgs a, int cell_blocks)
+{
+	const int K = a.n_bins, N = a.n;
+	const size_t KN = (size_t)K * N;
+
+	if ((int)blockIdx.x < cell_blocks) {
+		const size_t cell = (size_t)blockIdx.x * UPD_THREADS + threadIdx.x;
+		if (cell >= KN)
+			return;
+		float hv = a.hist[cell];
+		bool dirty = false;
+		for (int c0 = 0; c0 < a.n_calls; c0 += UPD_GROUP) {
+			unsigned hc[UPD_GROUP];
+			float2 de[UPD_GROUP];
+#pragma unroll
+			for (int g = 0; g < UPD_GROUP; g++) {
+				hc[g] = 0;
+				if (c0 + g < a.n_calls) {
+					const unsigned short *p = a.cnt + (size_t)(c0 + g) * a.splits * KN + cell;
+					for (int s = 0; s < a.splits; s++)
+						hc[g] += __ldcg(p + (size_t)s * KN);
+				}
+			}
+#pragma unroll
+			for (int g = 0; g < UPD_GROUP; g++)
+				de[g] = __ldg(&a.lut[hc[g]]);
+#pragma unroll
+			for (int g = 0; g < UPD_GROUP; g++) {
+				if (c0 + g >= a.n_calls)
+					break;
+				if (hv <= 0.01f && hc[g] == 0)          /* display.cl:237-238 */
+					continue;
+				hv = __fadd_rn(__fmul_rn(__fsub_rn(hv, de[g].x), de[g].y), de[g].x);   /* :247 */
+				hv = fminf(fmaxf(hv, 0.0f), 1.0f);                                      /* :250 */
+				dirty = true;
+			}
+		}
+		if (dirty)
+			a.hist[cell] = hv;
+		return;
+	}
+
+	const int col = ((int)blockIdx.x - cell_blocks) * UPD_THREADS + threadIdx.x;
+	if (col >= N)
+		return;
+	const int half = N >> 1;
+	const int i = col ^ half;                                 /* display.cl:201 */
+	const float xpos = ((float)i / (float)half) - 1.0f;       /* :209 */
+	float y = a.spectrum[i].y;
+	float m = a.spectrum[N + i].y;
+	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
+	for (int c = 0; c < a.n_calls; c++) {
+		float sum = 0.0f, bmax = -1000.0f;
+		for (int b = 0; b < blocks_per_call; b++) {
+			const size_t o = (size_t)(c * blocks_per_call + b) * N + col;
+			sum += __ldcg(&a.part_live[o]);
+			bmax = fmaxf(bmax, __ldcg(&a.part_max[o]));
+		}
 		/* live spectrum, display.cl:203-214 */
-		float y = a.spectrum[i].y;
 		if (!isfinite(y))
 			y = sum / (float)REF_ROWS;
 		y = __fadd_rn(__fmul_rn(y, a.live_carry), __fmul_rn(sum, a.alpha));
-		a.spectrum[i] = make_float2(xpos, y);
-
 		/* max hold with decay, display.cl:287-309 */
-		float m = a.spectrum[N + i].y;
 		if (!isfinite(m))
 			m = -FLT_MAX;
 		m = __fadd_rn(__fmul_rn(m, a.mh_keep), __fmul_rn(a.mh_mix, y));
 		m = fmaxf(m, bmax);
+	}
+	if (a.n_calls > 0) {
+		a.spectrum[i] = make_float2(xpos, y);
 		a.spectrum[N + i] = make_float2(xpos, m);
 	}
 }

@@ -30,7 +30,8 @@ namespace {
 enum { ST_BOOTING = 0, ST_PENDING, ST_READY };   /* cl.c:95-99 */
 
 constexpr int N_TABLES = 8;      /* cached (weights, lut) sets, one per distinct batch size */
-constexpr int MAX_SPLITS = 64;
+constexpr int MAX_SLICES = 128;  /* (call, row-split) slices folded by one count/update launch pair */
+constexpr size_t CNT_BUDGET = (size_t)1 << 30;   /* bytes of u16 hit-count slices kept on the device */
 
 struct BatchTables {
 	int batch = -1;
@@ -58,16 +59,19 @@ struct fosphor_cu {
 	float *d_wf = nullptr;
 	float *d_hist = nullptr;
 	float2 *d_spec = nullptr;
-	unsigned *d_ghits = nullptr;
-	float *d_part_live = nullptr, *d_part_max = nullptr;
-	unsigned *d_tickets = nullptr;
+	unsigned short *d_cnt = nullptr;     /* [max_slices][K][N] */
+	float *d_part_live = nullptr, *d_part_max = nullptr;   /* [max_slices][N] */
+	int max_slices = 0;
 
 	/* host-sample staging (fosphor_cu_process_host*) */
 	size_t stage_elems = 0;              /* complex samples per slot */
 	float2 *h_in[2] = {nullptr, nullptr};
 	float2 *d_in[2] = {nullptr, nullptr};
-	cudaEvent_t in_done[2] = {nullptr, nullptr};
+	cudaStream_t copy_stream = nullptr;  /* H2D of samples, overlaps the compute stream */
+	cudaEvent_t copied[2] = {nullptr, nullptr};     /* H2D into slot done (copy stream)   */
+	cudaEvent_t slot_free[2] = {nullptr, nullptr};  /* kernels that read the slot done    */
 	int slot = 0;
+	int last_slot = -1;
 	float *h_win = nullptr;              /* pinned copy of the window */
 	cudaEvent_t win_done = nullptr;
 
@@ -78,11 +82,13 @@ struct fosphor_cu {
 	BatchTables tables[N_TABLES];
 	unsigned long long use_clock = 0;
 	unsigned long long launches = 0;
+	int fft_variant = 1;                 /* 1: TMA-prefetching persistent kernel where applicable
+	                                      * 0: plain kernel (env FOSPHOR_B200_FFT_VARIANT=0)  */
 
 	/* optional per-kernel timing (bench.py roofline): event pairs around launches */
 	bool profiling = false;
-	std::vector<cudaEvent_t> prof_ev[2][2];   /* [kernel: 0 fft, 1 accumulate][begin/end] */
-	size_t prof_used[2] = {0, 0};
+	std::vector<cudaEvent_t> prof_ev[3][2];   /* [kernel: 0 fft, 1 count, 2 update][begin/end] */
+	size_t prof_used[3] = {0, 0, 0};
 
 	char err[256] = {0};
 };
@@ -194,8 +200,39 @@ bool plan_supported(int n)
 	return n == 512 || n == 1024 || n == 2048 || n == 4096 || n == 8192 || n == 16384;
 }
 
+template <class P>
+cudaError_t stream_setup()
+{
+	return cudaFuncSetAttribute(fft_power_stream_kernel<P>,
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamCfg<P>::SMEM);
+}
+
+template <class P>
+cudaError_t stream_launch(fosphor_cu *e, const float2 *in, long long hop, int wf_pos, int n_spectra)
+{
+	using C = StreamCfg<P>;
+	int grid = (n_spectra + C::WARPS - 1) / C::WARPS;
+	const int resident = e->sm_count * C::CTAS_PER_SM;
+	if (grid > resident)
+		grid = resident;                 /* persistent warps, grid-stride over spectra */
+	prof_mark(e, 0, 0);
+	fft_power_stream_kernel<P><<<grid, C::THREADS, C::SMEM, e->stream>>>(
+		in, hop, e->d_win, e->d_tw, e->d_wf, wf_pos, e->p.wf_rows - 1, n_spectra);
+	prof_mark(e, 0, 1);
+	e->launches++;
+	return cudaGetLastError();
+}
+
 cudaError_t launch_fft(fosphor_cu *e, const float2 *in, long long hop, int wf_pos, int n_spectra)
 {
+	/* TMA bulk copies need 16-byte aligned spectra */
+	const bool aligned = ((reinterpret_cast<unsigned long long>(in) & 15ull) == 0) && ((hop & 1) == 0);
+	if (aligned && e->fft_variant != 0) {
+		if (e->p.fft_len == 1024)
+			return stream_launch<Plan1024>(e, in, hop, wf_pos, n_spectra);
+		if (e->p.fft_len == 512)
+			return stream_launch<Plan512>(e, in, hop, wf_pos, n_spectra);
+	}
 	cudaError_t err = cudaErrorInvalidValue;
 	PLAN_SWITCH(e->p.fft_len, (err = plan_launch<P, false>(e, in, hop, wf_pos, nullptr, n_spectra)));
 	return err;
@@ -246,22 +283,26 @@ int get_tables(fosphor_cu *e, int batch, BatchTables **out)
 	return 0;
 }
 
-int choose_splits(const fosphor_cu *e, int batch, int *rows_per_split)
+/* How the calls of one launch are cut into slices (CTAs along the row axis).
+ * Only hit counts (integers) and per-ROWBLOCK partial sums cross slice
+ * boundaries, so the results are bit-identical for any slicing; the choice is
+ * purely about filling the chip: at least ~2 CTAs per SM when there is work. */
+void choose_slicing(const fosphor_cu *e, int n_calls, int batch, int *splits, int *rows_per_split)
 {
 	const int tiles = e->p.fft_len / ACC_COLS;
 	const int target = 2 * e->sm_count;
-	int s = (target + tiles - 1) / tiles;
-	const int max_s = batch / 16 > 0 ? batch / 16 : 1;
-	if (s > max_s) s = max_s;
-	if (s > MAX_SPLITS) s = MAX_SPLITS;
+	const int blocks = (batch + ROWBLOCK - 1) / ROWBLOCK;
+	int s = (target + tiles * n_calls - 1) / (tiles * n_calls);
+	if (s > blocks) s = blocks;
+	if (s > e->max_slices / n_calls) s = e->max_slices / n_calls;
 	if (s < 1) s = 1;
-	int rows = (batch + s - 1) / s;
-	rows = (rows + ACC_WARPS - 1) / ACC_WARPS * ACC_WARPS;
+	const int rows = (blocks + s - 1) / s * ROWBLOCK;
 	*rows_per_split = rows;
-	return (batch + rows - 1) / rows;
+	*splits = (batch + rows - 1) / rows;
 }
 
-int launch_accumulate(fosphor_cu *e, int wf_pos, int batch)
+/* fold n_calls calls (rows wf_pos .. wf_pos + n_calls*batch of the ring) into the state */
+int launch_accumulate(fosphor_cu *e, int wf_pos, int n_calls, int batch)
 {
 	BatchTables *t;
 	int rc = get_tables(e, batch, &t);
@@ -272,10 +313,9 @@ int launch_accumulate(fosphor_cu *e, int wf_pos, int batch)
 	a.wf = e->d_wf;
 	a.hist = e->d_hist;
 	a.spectrum = e->d_spec;
-	a.ghits = e->d_ghits;
+	a.cnt = e->d_cnt;
 	a.part_live = e->d_part_live;
 	a.part_max = e->d_part_max;
-	a.tickets = e->d_tickets;
 	a.weights = t->d_weights;
 	a.lut = t->d_lut;
 	a.n = e->p.fft_len;
@@ -283,7 +323,8 @@ int launch_accumulate(fosphor_cu *e, int wf_pos, int batch)
 	a.wf_mask = e->p.wf_rows - 1;
 	a.wf_pos = wf_pos;
 	a.batch = batch;
-	a.splits = choose_splits(e, batch, &a.rows_per_split);
+	a.n_calls = n_calls;
+	choose_slicing(e, n_calls, batch, &a.splits, &a.rows_per_split);
 	a.hscale = e->histo_scale;
 	a.hofs = e->histo_ofs;
 	a.alpha = e->p.live_alpha;
@@ -291,12 +332,18 @@ int launch_accumulate(fosphor_cu *e, int wf_pos, int batch)
 	a.mh_keep = e->p.maxhold_keep;
 	a.mh_mix = e->p.maxhold_mix;
 
-	const dim3 grid(e->p.fft_len / ACC_COLS, a.splits);
+	const dim3 grid(e->p.fft_len / ACC_COLS, n_calls * a.splits);
 	const size_t smem = sizeof(unsigned) * 32 * (size_t)e->p.n_bins;
 	prof_mark(e, 1, 0);
-	accumulate_kernel<<<grid, ACC_THREADS, smem, e->stream>>>(a);
+	count_kernel<<<grid, ACC_THREADS, smem, e->stream>>>(a);
 	prof_mark(e, 1, 1);
-	e->launches++;
+	const size_t cells = (size_t)e->p.n_bins * e->p.fft_len;
+	const int cell_blocks = (int)((cells + UPD_THREADS - 1) / UPD_THREADS);
+	const int col_blocks = (e->p.fft_len + UPD_THREADS - 1) / UPD_THREADS;
+	prof_mark(e, 2, 0);
+	update_kernel<<<cell_blocks + col_blocks, UPD_THREADS, 0, e->stream>>>(a, cell_blocks);
+	prof_mark(e, 2, 1);
+	e->launches += 2;
 	CU_CHECK(e, cudaGetLastError());
 	return 0;
 }
@@ -334,32 +381,66 @@ int process_device_calls(fosphor_cu *e, const float2 *in, int n_calls, int batch
 			return rc;
 	}
 	if (batch > 0) {
-		const int calls_per_chunk = e->p.wf_rows / batch;    /* >= 1: wf_rows >= batch_max */
+		/* a chunk = calls whose rows fit the ring and whose slices fit the count buffer */
+		int calls_per_chunk = e->p.wf_rows / batch;          /* >= 1: wf_rows >= batch_max */
+		if (calls_per_chunk > e->max_slices)
+			calls_per_chunk = e->max_slices;
 		for (int c0 = 0; c0 < n_calls; c0 += calls_per_chunk) {
 			const int nc = n_calls - c0 < calls_per_chunk ? n_calls - c0 : calls_per_chunk;
 			CU_CHECK(e, launch_fft(e, in + (long long)c0 * batch * hop, hop, e->wf_pos, nc * batch));
-			for (int c = 0; c < nc; c++) {
-				int rc = launch_accumulate(e, e->wf_pos, batch);
-				if (rc)
-					return rc;
-				e->wf_pos = (e->wf_pos + batch) & (e->p.wf_rows - 1);   /* cl.c:954 */
-			}
+			int rc = launch_accumulate(e, e->wf_pos, nc, batch);
+			if (rc)
+				return rc;
+			e->wf_pos = (e->wf_pos + nc * batch) & (e->p.wf_rows - 1);   /* cl.c:954, nc times */
 		}
 	}
 	e->state = ST_PENDING;                /* cl.c:957 */
 	return 0;
 }
 
+bool is_pinned_host(const void *p)
+{
+	cudaPointerAttributes attr;
+	if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return attr.type == cudaMemoryTypeHost;
+}
+
+/* Host samples -> device slot.  The source buffer is free when this returns
+ * (reference contract, base_sink_c_impl.cc:170-174): pageable sources are
+ * copied into a pinned staging slot by the CPU; page-locked sources
+ * (cudaHostAlloc / cudaHostRegister, e.g. a pinned FIFO) are DMA'd directly and
+ * only that copy is waited for.  Either way the H2D runs on its own stream and
+ * overlaps the kernels of the previous call. */
 int upload_staged(fosphor_cu *e, const float2 *src, size_t n_samples, float2 **dev_out)
 {
 	const int s = e->slot;
 	e->slot ^= 1;
-	CU_CHECK(e, cudaEventSynchronize(e->in_done[s]));
-	memcpy(e->h_in[s], src, sizeof(float2) * n_samples);
-	CU_CHECK(e, cudaMemcpyAsync(e->d_in[s], e->h_in[s], sizeof(float2) * n_samples,
-	                            cudaMemcpyHostToDevice, e->stream));
-	CU_CHECK(e, cudaEventRecord(e->in_done[s], e->stream));
+	const size_t bytes = sizeof(float2) * n_samples;
+	CU_CHECK(e, cudaEventSynchronize(e->slot_free[s]));     /* previous reader of d_in[s] done */
+	if (is_pinned_host(src)) {
+		CU_CHECK(e, cudaMemcpyAsync(e->d_in[s], src, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+		CU_CHECK(e, cudaEventRecord(e->copied[s], e->copy_stream));
+		CU_CHECK(e, cudaEventSynchronize(e->copied[s]));
+	} else {
+		memcpy(e->h_in[s], src, bytes);
+		CU_CHECK(e, cudaMemcpyAsync(e->d_in[s], e->h_in[s], bytes, cudaMemcpyHostToDevice, e->copy_stream));
+		CU_CHECK(e, cudaEventRecord(e->copied[s], e->copy_stream));
+	}
+	CU_CHECK(e, cudaStreamWaitEvent(e->stream, e->copied[s], 0));
+	e->last_slot = s;
 	*dev_out = e->d_in[s];
+	return 0;
+}
+
+int release_slot(fosphor_cu *e)
+{
+	if (e->last_slot >= 0) {
+		CU_CHECK(e, cudaEventRecord(e->slot_free[e->last_slot], e->stream));
+		e->last_slot = -1;
+	}
 	return 0;
 }
 
@@ -393,20 +474,22 @@ void fosphor_cu_destroy(struct fosphor_cu *e)
 	if (e->stream)
 		cudaStreamSynchronize(e->stream);
 	cudaFree(e->d_win); cudaFree(e->d_tw); cudaFree(e->d_wf); cudaFree(e->d_hist);
-	cudaFree(e->d_spec); cudaFree(e->d_ghits); cudaFree(e->d_part_live);
-	cudaFree(e->d_part_max); cudaFree(e->d_tickets);
+	cudaFree(e->d_spec); cudaFree(e->d_cnt); cudaFree(e->d_part_live);
+	cudaFree(e->d_part_max);
 	for (int i = 0; i < 2; i++) {
 		cudaFreeHost(e->h_in[i]);
 		cudaFree(e->d_in[i]);
-		if (e->in_done[i]) cudaEventDestroy(e->in_done[i]);
+		if (e->copied[i]) cudaEventDestroy(e->copied[i]);
+		if (e->slot_free[i]) cudaEventDestroy(e->slot_free[i]);
 	}
+	if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
 	cudaFreeHost(e->h_win);
 	if (e->win_done) cudaEventDestroy(e->win_done);
 	for (auto &t : e->tables) {
 		cudaFree(t.d_weights); cudaFree(t.d_lut); cudaFreeHost(t.h_stage);
 		if (t.uploaded) cudaEventDestroy(t.uploaded);
 	}
-	for (int k = 0; k < 2; k++)
+	for (int k = 0; k < 3; k++)
 		for (int j = 0; j < 2; j++)
 			for (cudaEvent_t ev : e->prof_ev[k][j])
 				cudaEventDestroy(ev);
@@ -422,7 +505,7 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 	const fosphor_cu_params &p = *pp;
 	if (!plan_supported(p.fft_len) || p.n_bins < 2 || p.n_bins > 4096 ||
 	    p.wf_rows < 1 || (p.wf_rows & (p.wf_rows - 1)) ||
-	    p.batch_mult < 1 || p.batch_max < p.batch_mult || p.batch_max % p.batch_mult ||
+	    p.batch_mult < 1 || p.batch_max < p.batch_mult || p.batch_max % p.batch_mult || p.batch_max > 32768 ||
 	    p.wf_rows < p.batch_max || !(p.histo_t0r > 0.0f) || !(p.histo_t0d > 0.0f))
 		return fail(nullptr, -EINVAL, "unsupported engine parameters (N=%d K=%d W=%d batch %d/%d)",
 		            p.fft_len, p.n_bins, p.wf_rows, p.batch_mult, p.batch_max);
@@ -469,12 +552,23 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 	CREATE_CHECK(cudaMalloc(&e->d_wf, sizeof(float) * w * n));
 	CREATE_CHECK(cudaMalloc(&e->d_hist, sizeof(float) * k * n));
 	CREATE_CHECK(cudaMalloc(&e->d_spec, sizeof(float2) * 2 * n));
-	CREATE_CHECK(cudaMalloc(&e->d_ghits, sizeof(unsigned) * k * n));
-	CREATE_CHECK(cudaMalloc(&e->d_part_live, sizeof(float) * MAX_SPLITS * n));
-	CREATE_CHECK(cudaMalloc(&e->d_part_max, sizeof(float) * MAX_SPLITS * n));
-	CREATE_CHECK(cudaMalloc(&e->d_tickets, sizeof(unsigned) * (n / ACC_COLS)));
-	CREATE_CHECK(cudaMemset(e->d_ghits, 0, sizeof(unsigned) * k * n));
-	CREATE_CHECK(cudaMemset(e->d_tickets, 0, sizeof(unsigned) * (n / ACC_COLS)));
+	{
+		/* slices: at least what one call needs to fill the chip, at most MAX_SLICES,
+		 * within CNT_BUDGET bytes of u16 counts */
+		const int tiles = p.fft_len / ACC_COLS;
+		int need = (2 * e->sm_count + tiles - 1) / tiles;
+		if (need < 1) need = 1;
+		size_t fit = CNT_BUDGET / (sizeof(unsigned short) * k * n);
+		int ms = fit > (size_t)MAX_SLICES ? MAX_SLICES : (int)fit;
+		if (ms < need) ms = need;
+		e->max_slices = ms;
+	}
+	CREATE_CHECK(cudaMalloc(&e->d_cnt, sizeof(unsigned short) * k * n * e->max_slices));
+	{
+		const size_t blocks = (size_t)(p.batch_max + ROWBLOCK - 1) / ROWBLOCK * e->max_slices;
+		CREATE_CHECK(cudaMalloc(&e->d_part_live, sizeof(float) * blocks * n));
+		CREATE_CHECK(cudaMalloc(&e->d_part_max, sizeof(float) * blocks * n));
+	}
 	CREATE_CHECK(cudaMemset(e->d_hist, 0, sizeof(float) * k * n));
 	CREATE_CHECK(cudaMemset(e->d_wf, 0, sizeof(float) * w * n));
 	CREATE_CHECK(cudaMemset(e->d_spec, 0, sizeof(float2) * 2 * n));
@@ -494,8 +588,14 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 		cudaError_t perr = cudaErrorInvalidValue;
 		PLAN_SWITCH(p.fft_len, (perr = plan_setup<P>()));
 		CREATE_CHECK(perr);
+		if (p.fft_len == 1024)
+			CREATE_CHECK(stream_setup<Plan1024>());
+		if (p.fft_len == 512)
+			CREATE_CHECK(stream_setup<Plan512>());
+		if (const char *v = getenv("FOSPHOR_B200_FFT_VARIANT"))
+			e->fft_variant = atoi(v);
 	}
-	CREATE_CHECK(cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	CREATE_CHECK(cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                                  (int)(sizeof(unsigned) * 32 * k)));
 
 	for (auto &t : e->tables) {
@@ -509,8 +609,10 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 	for (int i = 0; i < 2; i++) {
 		CREATE_CHECK(cudaMallocHost(&e->h_in[i], sizeof(float2) * e->stage_elems));
 		CREATE_CHECK(cudaMalloc(&e->d_in[i], sizeof(float2) * e->stage_elems));
-		CREATE_CHECK(cudaEventCreateWithFlags(&e->in_done[i], cudaEventDisableTiming));
+		CREATE_CHECK(cudaEventCreateWithFlags(&e->copied[i], cudaEventDisableTiming));
+		CREATE_CHECK(cudaEventCreateWithFlags(&e->slot_free[i], cudaEventDisableTiming));
 	}
+	CREATE_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
 #undef CREATE_CHECK
 
 	*out = e;
@@ -579,7 +681,10 @@ int fosphor_cu_process_host(struct fosphor_cu *e, const void *samples_host, int 
 		if (rc)
 			return rc;
 	}
-	return process_device_calls(e, dev, 1, len / n, n);
+	int rc = process_device_calls(e, dev, 1, len / n, n);
+	if (rc)
+		return rc;
+	return release_slot(e);
 }
 
 int fosphor_cu_process_host_raw(struct fosphor_cu *e, const void *raw_host,
@@ -605,6 +710,9 @@ int fosphor_cu_process_host_raw(struct fosphor_cu *e, const void *raw_host,
 		if (rc)
 			return rc;
 		rc = process_device_calls(e, dev, (int)nc, batch, hop);
+		if (rc)
+			return rc;
+		rc = release_slot(e);
 		if (rc)
 			return rc;
 	}
@@ -688,28 +796,27 @@ int fosphor_cu_profile(struct fosphor_cu *e, int enable)
 		return -EINVAL;
 	CU_CHECK(e, cudaStreamSynchronize(e->stream));
 	e->profiling = enable != 0;
-	e->prof_used[0] = e->prof_used[1] = 0;
+	e->prof_used[0] = e->prof_used[1] = e->prof_used[2] = 0;
 	return 0;
 }
 
-int fosphor_cu_profile_read(struct fosphor_cu *e, double *fft_ms, unsigned long long *fft_launches,
-                            double *acc_ms, unsigned long long *acc_launches)
+int fosphor_cu_profile_read(struct fosphor_cu *e, double *ms_out, unsigned long long *launches_out)
 {
 	if (!e)
 		return -EINVAL;
 	CU_CHECK(e, cudaStreamSynchronize(e->stream));
-	double ms[2] = {0.0, 0.0};
-	for (int k = 0; k < 2; k++)
+	double ms[3] = {0.0, 0.0, 0.0};
+	for (int k = 0; k < 3; k++)
 		for (size_t i = 0; i < e->prof_used[k]; i++) {
 			float t = 0.0f;
 			CU_CHECK(e, cudaEventElapsedTime(&t, e->prof_ev[k][0][i], e->prof_ev[k][1][i]));
 			ms[k] += t;
 		}
-	if (fft_ms) *fft_ms = ms[0];
-	if (fft_launches) *fft_launches = e->prof_used[0];
-	if (acc_ms) *acc_ms = ms[1];
-	if (acc_launches) *acc_launches = e->prof_used[1];
-	e->prof_used[0] = e->prof_used[1] = 0;
+	for (int k = 0; k < 3; k++) {
+		if (ms_out) ms_out[k] = ms[k];
+		if (launches_out) launches_out[k] = e->prof_used[k];
+		e->prof_used[k] = 0;
+	}
 	return 0;
 }
 

@@ -55,7 +55,11 @@ __device__ __forceinline__ float log_power(float2 x)
 {
 	/* display.cl:136: log10(hypot(re, im)).  re^2+im^2 cannot overflow for
 	 * |x| < 1.8e19, far above any windowed sum of [-1,1] IQ samples. */
-	return __log2f(fmaf(x.x, x.x, x.y * x.y)) * FOSPHOR_HALF_LOG10_2;
+	float l;
+	/* MUFU.LG2 without the denormal pre-scaling of __log2f: |X|^2 < 1.2e-38
+	 * (|X| < 1e-19) is treated as 0 -> -inf, far below any displayable level */
+	asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaf(x.x, x.x, x.y * x.y)));
+	return l * FOSPHOR_HALF_LOG10_2;
 }
 
 template <class P>
@@ -161,6 +165,164 @@ fft_power_kernel(const float2 *__restrict__ in, long long hop,
 			constexpr int t = decltype(tc)::value;
 			store_bin(i + t * P::NB1, v[brev<R1>(t)]);
 		});
+	}
+}
+
+/* ------------------------------------------------------------------------ */
+/* Streaming variant for the one-warp-per-spectrum plans (N = 512, 1024)      */
+/* ------------------------------------------------------------------------ */
+/*
+ * Same arithmetic as fft_power_kernel (bit-identical results), different data
+ * movement: warps are persistent and each one double-buffers its input with
+ * the TMA bulk-copy engine (cp.async.bulk global -> shared, completion on an
+ * mbarrier), so the 8 KB of the NEXT spectrum are in flight while the current
+ * one is being transformed.  ncu of the plain kernel showed it latency bound
+ * (long-scoreboard + LSU-queue stalls, 47 % issue utilisation, 32 % of HBM
+ * peak); here no thread ever waits on a global load in steady state and the
+ * load instructions leave the LSU queue altogether.  The buffer that held the
+ * inputs of the current spectrum is reused as the padded exchange buffer
+ * between the two passes, so a warp needs 2 x SM_ELEMS float2 of shared memory.
+ * The window lives in registers for the lifetime of the warp.
+ * Requires 16-byte aligned spectra: even hop and 16-byte aligned base.
+ */
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+	return (unsigned)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity)
+{
+	unsigned ok;
+	asm volatile("{\n\t.reg .pred p;\n\t"
+	             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+	             "selp.u32 %0, 1, 0, p;\n\t}"
+	             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+	return ok != 0;
+}
+
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <class P>
+struct StreamCfg {
+	static_assert(P::NPASS == 2 && P::T == 32, "one warp per spectrum plans only");
+	static constexpr int WARPS = 4;
+	static constexpr int THREADS = WARPS * 32;
+	static constexpr int CTAS_PER_SM = 3;
+	static constexpr int BUF_ELEMS = P::SM_ELEMS;                 /* >= N: holds inputs, then the exchange */
+	static constexpr size_t SMEM = sizeof(float2) * (size_t)BUF_ELEMS * 2 * WARPS + 8 * 2 * WARPS;
+	static constexpr unsigned IN_BYTES = sizeof(float2) * P::N;
+};
+
+template <class P>
+__global__ void __launch_bounds__(StreamCfg<P>::THREADS, StreamCfg<P>::CTAS_PER_SM)
+fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
+                        const float *__restrict__ win, const float2 *__restrict__ tw,
+                        float *__restrict__ wf, int wf_pos, int wf_mask, int n_spectra)
+{
+	using C = StreamCfg<P>;
+	constexpr int N = P::N, R0 = P::R0, R1 = P::R1;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int gw = blockIdx.x * C::WARPS + warp;
+	const int G = gridDim.x * C::WARPS;
+
+	float2 *bufs = reinterpret_cast<float2 *>(smem_raw) + (size_t)warp * 2 * C::BUF_ELEMS;
+	unsigned long long *bars = reinterpret_cast<unsigned long long *>(
+		smem_raw + sizeof(float2) * (size_t)C::BUF_ELEMS * 2 * C::WARPS) + warp * 2;
+	const unsigned bar0 = smem_u32(bars), buf0 = smem_u32(bufs);
+	constexpr unsigned BUF_BYTES = sizeof(float2) * C::BUF_ELEMS;
+
+	if (lane == 0) {
+		mbar_init(bar0, 1);
+		mbar_init(bar0 + 8, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+
+	/* window slice of this lane: pass 0 element (lane + t*NB0) for the R0 registers */
+	float wreg[R0];
+	if (lane < P::NB0) {
+#pragma unroll
+		for (int t = 0; t < R0; t++)
+			wreg[t] = __ldg(&win[lane + t * P::NB0]);
+	}
+
+	int s = gw;
+	if (s < n_spectra && lane == 0) {
+		mbar_expect_tx(bar0, C::IN_BYTES);
+		bulk_g2s(buf0, in + (long long)s * hop, C::IN_BYTES, bar0);
+	}
+	unsigned phases = 0u;                /* bit b = parity to wait for on barrier b */
+
+	for (int it = 0; s < n_spectra; it++, s += G) {
+		const int b = it & 1;
+		float2 *buf = bufs + (size_t)b * C::BUF_ELEMS;
+
+		/* prefetch the next spectrum into the other buffer (last touched by this
+		 * warp's generic-proxy loads/stores one iteration ago) */
+		__syncwarp();
+		if (lane == 0 && s + G < n_spectra) {
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			const unsigned nb = (unsigned)(b ^ 1);
+			mbar_expect_tx(bar0 + 8 * nb, C::IN_BYTES);
+			bulk_g2s(buf0 + nb * BUF_BYTES, in + (long long)(s + G) * hop, C::IN_BYTES, bar0 + 8 * nb);
+		}
+
+		while (!mbar_try_wait(bar0 + 8 * b, (phases >> b) & 1u)) { }
+		phases ^= 1u << b;
+
+		float *row = wf + (size_t)((wf_pos + s) & wf_mask) * N;
+
+		/* ---- pass 0 ---- */
+		float2 v0[R0];
+		if (lane < P::NB0) {
+#pragma unroll
+			for (int t = 0; t < R0; t++) {
+				const float2 x = buf[lane + t * P::NB0];
+				v0[t] = make_float2(x.x * wreg[t], x.y * wreg[t]);   /* fft.cl:416-417 */
+			}
+		}
+		__syncwarp();                   /* inputs consumed: buf becomes the exchange buffer */
+		if (lane < P::NB0) {
+			dif<R0>(v0);
+			static_for<0, R0>([&](auto tc) {
+				constexpr int t = decltype(tc)::value;
+				buf[pad_idx<P>(lane * R0 + t)] = v0[brev<R0>(t)];
+			});
+		}
+		__syncwarp();
+
+		/* ---- pass 1 (P = R0), last ---- */
+		if (lane < P::NB1) {
+			const int k = lane & (R0 - 1);
+			float2 v[R1];
+#pragma unroll
+			for (int t = 0; t < R1; t++)
+				v[t] = buf[pad_idx<P>(lane + t * P::NB1)];
+#pragma unroll
+			for (int t = 1; t < R1; t++)
+				v[t] = cmul(v[t], __ldg(&tw[t * R0 + k]));
+			dif<R1>(v);
+			static_for<0, R1>([&](auto tc) {
+				constexpr int t = decltype(tc)::value;
+				row[lane + t * P::NB1] = log_power(v[brev<R1>(t)]);
+			});
+		}
 	}
 }
 

@@ -56,8 +56,7 @@ def load_library(path=None):
     L.fosphor_cu_export_maxhold.argtypes = [vp, vp]
     L.fosphor_cu_debug_fft.argtypes = [vp, vp, C.c_int, ll, vp]
     L.fosphor_cu_profile.argtypes = [vp, C.c_int]
-    L.fosphor_cu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong),
-                                          C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
+    L.fosphor_cu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
     L.fosphor_cu_launch_count.argtypes = [vp]
     L.fosphor_cu_launch_count.restype = C.c_ulonglong
     L.fosphor_cu_last_error.argtypes = [vp]
@@ -163,6 +162,11 @@ class Fosphor:
         rc = self._chk(self.lib.fosphor_cu_finish(self.h, *ptrs))
         return rc, self._host
 
+    def finish_into(self, wf_ptr, hist_ptr, spec_ptr):
+        """finish() into caller-owned host memory (e.g. page-locked buffers); 0 pointers skip an array."""
+        return self._chk(self.lib.fosphor_cu_finish(self.h, C.c_void_p(wf_ptr or None),
+                                                    C.c_void_p(hist_ptr or None), C.c_void_p(spec_ptr or None)))
+
     def sync(self):
         return self._chk(self.lib.fosphor_cu_sync(self.h))
 
@@ -178,10 +182,11 @@ class Fosphor:
         return self._chk(self.lib.fosphor_cu_profile(self.h, int(enable)))
 
     def profile_read(self):
-        a, b = C.c_double(), C.c_double()
-        na, nb = C.c_ulonglong(), C.c_ulonglong()
-        self._chk(self.lib.fosphor_cu_profile_read(self.h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
-        return {"fft_ms": a.value, "fft_launches": na.value, "acc_ms": b.value, "acc_launches": nb.value}
+        ms = (C.c_double * 3)()
+        nl = (C.c_ulonglong * 3)()
+        self._chk(self.lib.fosphor_cu_profile_read(self.h, ms, nl))
+        return {"fft_ms": ms[0], "fft_launches": nl[0], "count_ms": ms[1], "count_launches": nl[1],
+                "update_ms": ms[2], "update_launches": nl[2]}
 
     def device_ptrs(self):
         return {n: getattr(self.lib, "fosphor_cu_device_" + n)(self.h)

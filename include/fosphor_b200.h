@@ -143,13 +143,13 @@ int fosphor_cu_export_maxhold(struct fosphor_cu *e, float *out_dev);
 int fosphor_cu_debug_fft(struct fosphor_cu *e, const void *samples_dev,
                          int n_spectra, long long hop, void *out_dev);
 
-/* Per-kernel device timing for the roofline report: when enabled, every FFT and
- * accumulate launch is bracketed by CUDA events on the engine stream.
- * profile_read() synchronises, returns the summed kernel durations (ms) and
- * launch counts since the last read, and resets the counters. */
+/* Per-kernel device timing for the roofline report: when enabled, every launch
+ * of the three hot kernels is bracketed by CUDA events on the engine stream.
+ * profile_read() synchronises, fills ms[3] / launches[3] (0 = fft_power,
+ * 1 = count, 2 = update) with the summed durations and launch counts since
+ * the last read, and resets the counters. */
 int fosphor_cu_profile(struct fosphor_cu *e, int enable);
-int fosphor_cu_profile_read(struct fosphor_cu *e, double *fft_ms, unsigned long long *fft_launches,
-                            double *acc_ms, unsigned long long *acc_launches);
+int fosphor_cu_profile_read(struct fosphor_cu *e, double *ms, unsigned long long *launches);
 
 /* Number of kernel launches issued by this engine so far. */
 unsigned long long fosphor_cu_launch_count(const struct fosphor_cu *e);

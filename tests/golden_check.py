@@ -40,5 +40,4 @@ def check_case(name, engine):
         rows = z[key + "_wf_rows"]
         parity.check_waterfall(r["waterfall"][rows], z[key + "_waterfall"])
         parity.check_histogram(r["histogram"], z[key + "_histogram"], hits_in_play=max(1, spectra_so_far) * 1024)
-        cols = parity.conditioned_columns(z[key + "_waterfall"])
-        parity.check_spectrum(r["spectrum"], z[key + "_spectrum"], cols=cols)
+        parity.check_spectrum(r["spectrum"], z[key + "_spectrum"], wf_ref=z[key + "_waterfall"])

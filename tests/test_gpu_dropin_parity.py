@@ -51,7 +51,7 @@ def test_dropin_side_by_side_with_live_reference():
         assert ra["wf_pos"] == rb["wf_pos"]
         parity.check_waterfall(rb["waterfall"], ra["waterfall"])
         parity.check_histogram(rb["histogram"], ra["histogram"], hits_in_play=max(1, spectra) * 1024)
-        parity.check_spectrum(rb["spectrum"], ra["spectrum"])
+        parity.check_spectrum(rb["spectrum"], ra["spectrum"], wf_ref=ra["waterfall"])
     ref.release()
     mine.release()
 

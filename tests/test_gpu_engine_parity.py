@@ -107,11 +107,12 @@ def test_cfg1_burst(torch_cuda, n_bins, via):
     """BASELINE.json configs[0]: N=1024, one 64k burst (128 bins = reference, 256 = BASELINE)."""
     x = signals.cfg1_burst()
     eng, host, orc = _run_both(torch_cuda, dict(n_bins=n_bins), [x], via)
-    parity.check_waterfall(host["waterfall"], orc.waterfall, rows=np.arange(64))
+    rows_written = np.arange(64)
+    parity.check_waterfall(host["waterfall"], orc.waterfall, rows=rows_written)
     # rows never written keep the first-use fill (cl.c:418-436)
     assert np.array_equal(host["waterfall"][64:], orc.waterfall[64:])
     parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=64 * 1024)
-    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    parity.check_spectrum(host["spectrum"], orc.spectrum, wf_ref=orc.waterfall[rows_written])
     eng.close()
 
 
@@ -125,9 +126,10 @@ def test_call_sequence_state(torch_cuda):
         calls.append(stream[pos:pos + b * n])
         pos += b * n
     eng, host, orc = _run_both(torch_cuda, dict(), calls)
+    rows_written = np.arange(1024)
     parity.check_waterfall(host["waterfall"], orc.waterfall)
     parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=sum(sizes) * n)
-    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    parity.check_spectrum(host["spectrum"], orc.spectrum, wf_ref=orc.waterfall[rows_written])
     eng.close()
 
 
@@ -147,9 +149,10 @@ def test_cfg3_persistence_stress(torch_cuda):
         assert eng.process_device(d_raw.data_ptr() + 8 * off, b, hop) == 0
     rc, host = eng.finish()
     orc.finish()
-    parity.check_waterfall(host["waterfall"], orc.waterfall, rows=np.arange(2 * b))
+    rows_written = np.arange(2 * b)
+    parity.check_waterfall(host["waterfall"], orc.waterfall, rows=rows_written)
     parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=2 * b * n)
-    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    parity.check_spectrum(host["spectrum"], orc.spectrum, wf_ref=orc.waterfall[rows_written])
     eng.close()
 
 
@@ -158,9 +161,10 @@ def test_cfg4_large(torch_cuda):
     n, k, b = 16384, 1024, 1024
     x = signals.noise_tones(n * b, n_fft=n, seed=10, sigma=0.02)
     eng, host, orc = _run_both(torch_cuda, dict(fft_len=n, n_bins=k, wf_rows=1024), [x])
+    rows_written = np.arange(1024)
     parity.check_waterfall(host["waterfall"], orc.waterfall)
     parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=b * n)
-    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    parity.check_spectrum(host["spectrum"], orc.spectrum, wf_ref=orc.waterfall[rows_written])
     eng.close()
 
 
@@ -170,9 +174,10 @@ def test_sweep_sizes(torch_cuda, n):
     b = 64
     x = signals.noise_tones(n * b, n_fft=n, seed=50 + n, sigma=0.02)
     eng, host, orc = _run_both(torch_cuda, dict(fft_len=n, n_bins=256, wf_rows=1024), [x])
-    parity.check_waterfall(host["waterfall"], orc.waterfall, rows=np.arange(b))
+    rows_written = np.arange(b)
+    parity.check_waterfall(host["waterfall"], orc.waterfall, rows=rows_written)
     parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=b * n)
-    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    parity.check_spectrum(host["spectrum"], orc.spectrum, wf_ref=orc.waterfall[rows_written])
     eng.close()
 
 
@@ -181,8 +186,9 @@ def test_dc_contention_and_zeros(torch_cuda):
     n, b = 1024, 256
     dc = np.full(n * b, 0.25 + 0.1j, np.complex64)
     eng, host, orc = _run_both(torch_cuda, dict(), [dc])
+    rows_written = np.arange(b)
     parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=b * n)
-    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    parity.check_spectrum(host["spectrum"], orc.spectrum, wf_ref=orc.waterfall[rows_written])
     eng.close()
 
     zeros = np.zeros(n * 16, np.complex64)
@@ -190,9 +196,10 @@ def test_dc_contention_and_zeros(torch_cuda):
     eng, host, orc = _run_both(torch_cuda, dict(), [zeros, data])
     wf = host["waterfall"]
     assert np.all(np.isneginf(wf[:16])) and np.all(np.isneginf(orc.waterfall[:16]))
-    parity.check_waterfall(wf, orc.waterfall, rows=np.arange(16, 48))
+    rows_written = np.arange(16, 48)
+    parity.check_waterfall(wf, orc.waterfall, rows=rows_written)
     parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=48 * n)
-    parity.check_spectrum(host["spectrum"], orc.spectrum)
+    parity.check_spectrum(host["spectrum"], orc.spectrum, wf_ref=orc.waterfall[rows_written])
     eng.close()
 
 
@@ -212,6 +219,25 @@ def test_validation_and_state_machine(torch_cuda):
     assert eng.waterfall_position == 16
     assert eng.finish()[0] == 1
     eng.close()
+
+
+def test_stream_kernel_equals_plain_kernel(torch_cuda, monkeypatch):
+    """The TMA-prefetching persistent FFT kernel and the plain one do the same
+    arithmetic: bit-identical waterfall / histogram / spectrum (N = 1024 and 512)."""
+    torch = torch_cuda
+    for n in (1024, 512):
+        x = signals.noise_tones(n * 1024, n_fft=n, seed=77)
+        d = _to_dev(torch, x)
+        outs = []
+        for variant in ("1", "0"):
+            monkeypatch.setenv("FOSPHOR_B200_FFT_VARIANT", variant)
+            e = _engine(fft_len=n, n_bins=256)
+            assert e.process_device(d.data_ptr(), 1024) == 0
+            _, h = e.finish()
+            outs.append({k: v.copy() for k, v in h.items()})
+            e.close()
+        for key in ("waterfall", "histogram", "spectrum"):
+            assert np.array_equal(outs[0][key], outs[1][key]), (n, key)
 
 
 # ---------------------------------------------------------------------------
@@ -252,6 +278,7 @@ def test_histogram_mass_property(torch_cuda):
     x = signals.noise_tones(n * b, seed=33)
     eng, host, orc = _run_both(torch_cuda, dict(n_bins=k), [x])
     hits = orc.last_hits
+    rows_written = np.arange(b)
     assert np.all(hits.sum(axis=0) == b)
     parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=b * n)
     # live IIR linearity in the carry: second identical call moves live towards the same mean
