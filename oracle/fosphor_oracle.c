@@ -1,7 +1,8 @@
 /*
  * fosphor_oracle.c - CPU restatement of fosphor's spectral hot path.
  *
- * TEST INFRASTRUCTURE ONLY ("parity unpinned", see fosphor_oracle.h).
+ * TEST INFRASTRUCTURE ONLY (pinned by golden vectors from the reference itself,
+ * see fosphor_oracle.h).
  * Written from the behaviour of the reference sources cited inline
  * (paths relative to the reference's lib/fosphor/ unless noted); it is not
  * a translation of the OpenCL kernels: the device code there is organised
