@@ -182,7 +182,8 @@ def run_b200(args):
     samples_per_step = spectra_per_step * n
     hop = n // OVERLAP
 
-    eng = Fosphor(fft_len=n, n_bins=k, wf_rows=WF_ROWS, device=local, stream=stream.cuda_stream)
+    wf_rows = args.wf_rows
+    eng = Fosphor(fft_len=n, n_bins=k, wf_rows=wf_rows, device=local, stream=stream.cuda_stream)
 
     # ---- inputs: two distinct seconds of signal, raw and pre-overlapped (3.2 GB each >> L2) ----
     pool_n = raw_pool_n = 2
@@ -255,6 +256,25 @@ def run_b200(args):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
+
+    # the same kernels timed without the count/update overlap (one stream), for reference
+    os.environ["FOSPHOR_B200_OVERLAP"] = "0"
+    eng_iso = Fosphor(fft_len=n, n_bins=k, wf_rows=wf_rows, device=local, stream=stream.cuda_stream)
+    os.environ.pop("FOSPHOR_B200_OVERLAP")
+    eng, eng_iso = eng_iso, eng
+    ms_iso = timed(lambda i: step_device(i, True), prof_steps, 2)
+    eng.profile(True)
+    timed(lambda i: step_device(i, True), prof_steps, 0)
+    prof_iso = eng.profile_read()
+    eng.profile(False)
+    eng.close()
+    eng = eng_iso
+    iso = {"ms_per_step": ms_iso / prof_steps,
+           "fft_ms_per_launch": prof_iso["fft_ms"] / max(1, prof_iso["fft_launches"]),
+           "count_ms_per_launch": prof_iso["count_ms"] / max(1, prof_iso["count_launches"]),
+           "update_ms_per_launch": prof_iso["update_ms"] / max(1, prof_iso["update_launches"]),
+           "fft_GBps": fft_kernel_bytes(n, spectra_per_step * prof_steps // max(1, prof_iso["fft_launches"]), 1.0)
+           / (prof_iso["fft_ms"] / max(1, prof_iso["fft_launches"]) * 1e-3) / 1e9}
 
     # ---- in-engine overlap variant (raw stream, hop = N/4) ----
     ms_hop = timed(lambda i: step_device(i, False), args.steps, args.warmup)
@@ -335,7 +355,7 @@ def run_b200(args):
             "config": {"workload": "cfg2: N=1024, 256 bins, overlap=4 (pre-overlapped stream, r=1), B=1024 "
                                    "spectra/call, step = 1 s of 100 Msps IQ = 384 calls = 393216 spectra",
                        "fft_len": n, "n_bins": k, "overlap": OVERLAP, "batch": b, "calls_per_step": calls,
-                       "wf_rows": WF_ROWS,
+                       "wf_rows": wf_rows,
                        "l2": "each step streams a %d MiB input (two alternating buffers), far larger than the 126 MB L2" % (samples_per_step * 8 // 2**20),
                        "multi_gpu": "one channel per GPU, NCCL max all-reduce of max-hold per step" if world > 1 else "single"},
             "gpu_launches": int(launches_timed),
@@ -346,6 +366,7 @@ def run_b200(args):
                          "bytes_per_launch": fft_bytes, "ms_per_launch": fft_ms,
                          "spectra_per_launch": spectra_per_fft_launch,
                          "count_ms_per_launch": count_ms, "update_ms_per_launch": update_ms,
+                         "single_stream": iso,
                          "step_algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                          "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e, "unit": "Mcomplex-samples/s",
@@ -429,6 +450,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--wf-rows", type=int, default=WF_ROWS, help="device waterfall ring rows (power of two)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -43,7 +43,6 @@ constexpr int ACC_COLS = 32;     /* columns per tile == warp width */
 constexpr int ACC_WARPS = 8;
 constexpr int ACC_THREADS = ACC_WARPS * 32;
 constexpr int UPD_THREADS = 256;
-constexpr int UPD_GROUP = 8;     /* calls whose loads are issued together */
 constexpr int REF_ROWS = 16;     /* display.cl:206-207 "sum / get_local_size(1)" */
 
 struct AccumArgs {
@@ -79,9 +78,37 @@ __device__ __forceinline__ int map_bin(float x, float kmaxf)
 	return (int)r;
 }
 
-constexpr int CNT_INFLIGHT = 8;   /* rows whose loads a warp issues before consuming any */
 constexpr int ROWBLOCK = 128;     /* canonical unit of the f32 live partial sums */
 constexpr int BLK_GROUP = 8;      /* row blocks reduced per pass through shared memory */
+
+struct RowCtx {
+	const float *base;        /* wf + column */
+	const float *weights;
+	unsigned *my_hits;        /* sh_hits + lane */
+	unsigned ring0, mask, n;
+	float hscale, hofs, kmaxf;
+};
+
+/* U rows (s, s+8, ..., one per CTA-wide stride) of one column per lane: all
+ * loads first, then the arithmetic; no bounds checks inside. */
+template <int U>
+__device__ __forceinline__ void count_rows(const RowCtx &c, int s, float &live, float &mx)
+{
+	float pw[U], wt[U];
+#pragma unroll
+	for (int u = 0; u < U; u++) {
+		const unsigned r = (c.ring0 + (unsigned)(s + u * ACC_WARPS)) & c.mask;
+		pw[u] = __ldcg(c.base + (size_t)(r * c.n));
+		wt[u] = __ldg(c.weights + s + u * ACC_WARPS);
+	}
+#pragma unroll
+	for (int u = 0; u < U; u++) {
+		live = fmaf(pw[u], wt[u], live);                                  /* display.cl:149-150 */
+		mx = fmaxf(mx, pw[u]);                                            /* :139 */
+		const int bin = map_bin(__fmul_rn(c.hscale, __fadd_rn(pw[u], c.hofs)), c.kmaxf);
+		atomicAdd(c.my_hits + bin * 32, 1u);                              /* :170-177 */
+	}
+}
 
 /* The f32 live-spectrum partial sums are formed per ROWBLOCK rows in a fixed
  * order (warp w takes rows w, w+8, ... of the block; the 8 warp partials are
@@ -110,11 +137,16 @@ count_kernel(const AccumArgs a)
 	/* rows [row0, row1) of this call; rows_per_split is a multiple of ROWBLOCK */
 	const int row0 = split * a.rows_per_split;
 	const int row1 = min(a.batch, row0 + a.rows_per_split);
-	const unsigned ring0 = (unsigned)(a.wf_pos + call * a.batch);
-	const unsigned mask = (unsigned)a.wf_mask;
-	const float *base = a.wf + col;
-	const float kmaxf = (float)(K - 1);
-	unsigned *my_hits = sh_hits + lane;
+	RowCtx c;
+	c.base = a.wf + col;
+	c.weights = a.weights;
+	c.my_hits = sh_hits + lane;
+	c.ring0 = (unsigned)(a.wf_pos + call * a.batch);
+	c.mask = (unsigned)a.wf_mask;
+	c.n = (unsigned)N;
+	c.hscale = a.hscale;
+	c.hofs = a.hofs;
+	c.kmaxf = (float)(K - 1);
 	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
 	const size_t part_base = (size_t)call * blocks_per_call;
 
@@ -124,26 +156,13 @@ count_kernel(const AccumArgs a)
 		for (int b0 = g0; b0 < g1; b0 += ROWBLOCK, nblk++) {
 			const int b1 = min(g1, b0 + ROWBLOCK);
 			float live = 0.0f, mx = -1000.0f;       /* display.cl:91,113 */
-			for (int s0 = b0 + warp; s0 < b1; s0 += ACC_WARPS * CNT_INFLIGHT) {
-				float pw[CNT_INFLIGHT], wt[CNT_INFLIGHT];
-#pragma unroll
-				for (int u = 0; u < CNT_INFLIGHT; u++) {
-					const int s = s0 + u * ACC_WARPS;
-					if (s < b1) {
-						pw[u] = __ldcg(base + (size_t)(((ring0 + (unsigned)s) & mask) * (unsigned)N));
-						wt[u] = __ldg(&a.weights[s]);
-					}
-				}
-#pragma unroll
-				for (int u = 0; u < CNT_INFLIGHT; u++) {
-					if (s0 + u * ACC_WARPS < b1) {
-						live = fmaf(pw[u], wt[u], live);                  /* :149-150 */
-						mx = fmaxf(mx, pw[u]);                            /* :139 */
-						const int bin = map_bin(__fmul_rn(a.hscale, __fadd_rn(pw[u], a.hofs)), kmaxf);
-						atomicAdd(my_hits + bin * 32, 1u);                /* :170-177 */
-					}
-				}
-			}
+			int s = b0 + warp;
+			for (; s + 7 * ACC_WARPS < b1; s += 8 * ACC_WARPS)
+				count_rows<8>(c, s, live, mx);
+			for (; s + ACC_WARPS < b1; s += 2 * ACC_WARPS)
+				count_rows<2>(c, s, live, mx);
+			if (s < b1)
+				count_rows<1>(c, s, live, mx);
 			sh_live[nblk][warp][lane] = live;
 			sh_max[nblk][warp][lane] = mx;
 		}
@@ -168,48 +187,65 @@ count_kernel(const AccumArgs a)
 		dst[(size_t)bin * N] = (unsigned short)sh_hits[bin * 32 + lane];
 }
 
-/* blocks [0, cell_blocks): one thread per histogram cell (bin-major, so a warp
- * touches 32 consecutive columns of one bin); blocks beyond: one thread per column. */
+constexpr int UPD_CELLS = 2;      /* adjacent cells per thread (one 32-bit load of two u16 counts) */
+constexpr int UPD_SLICES = 8;     /* slices whose loads are issued together */
+
+__device__ __forceinline__ float rise_decay(float hv, unsigned hc, const float2 *lut, bool &dirty)
+{
+	if (hv <= 0.01f && hc == 0)                             /* display.cl:237-238 */
+		return hv;
+	const float2 de = lut[hc];
+	hv = __fadd_rn(__fmul_rn(__fsub_rn(hv, de.x), de.y), de.x);       /* :247 */
+	dirty = true;
+	return fminf(fmaxf(hv, 0.0f), 1.0f);                              /* :250 */
+}
+
+/* blocks [0, cell_blocks): one thread per UPD_CELLS adjacent histogram cells
+ * (bin-major: a warp covers 64 consecutive columns of one bin); blocks beyond:
+ * one thread per column for live / max-hold.  N is even, so a cell pair never
+ * straddles two bins. */
 __global__ void __launch_bounds__(UPD_THREADS)
 update_kernel(const AccumArgs a, int cell_blocks)
 {
+	extern __shared__ float2 sh_lut[];              /* [B+1] (d, e) */
 	const int K = a.n_bins, N = a.n;
 	const size_t KN = (size_t)K * N;
 
 	if ((int)blockIdx.x < cell_blocks) {
-		const size_t cell = (size_t)blockIdx.x * UPD_THREADS + threadIdx.x;
+		for (int i = threadIdx.x; i <= a.batch; i += UPD_THREADS)
+			sh_lut[i] = __ldg(&a.lut[i]);
+		__syncthreads();
+		const size_t cell = ((size_t)blockIdx.x * UPD_THREADS + threadIdx.x) * UPD_CELLS;
 		if (cell >= KN)
 			return;
-		float hv = a.hist[cell];
+		float2 hv = *reinterpret_cast<const float2 *>(a.hist + cell);
 		bool dirty = false;
-		for (int c0 = 0; c0 < a.n_calls; c0 += UPD_GROUP) {
-			unsigned hc[UPD_GROUP];
-			float2 de[UPD_GROUP];
+		const int total = a.n_calls * a.splits;
+		const unsigned *cnt = reinterpret_cast<const unsigned *>(a.cnt + cell);   /* 2 x u16 */
+		const size_t stride = KN / 2;                                              /* in 32-bit words */
+		unsigned hc0 = 0, hc1 = 0;
+		int in_call = 0;
+		for (int j0 = 0; j0 < total; j0 += UPD_SLICES) {
+			unsigned w[UPD_SLICES];
 #pragma unroll
-			for (int g = 0; g < UPD_GROUP; g++) {
-				hc[g] = 0;
-				if (c0 + g < a.n_calls) {
-					const unsigned short *p = a.cnt + (size_t)(c0 + g) * a.splits * KN + cell;
-					for (int s = 0; s < a.splits; s++)
-						hc[g] += __ldcg(p + (size_t)s * KN);
+			for (int u = 0; u < UPD_SLICES; u++)
+				w[u] = (j0 + u < total) ? __ldcg(cnt + (size_t)(j0 + u) * stride) : 0u;
+#pragma unroll
+			for (int u = 0; u < UPD_SLICES; u++) {
+				if (j0 + u < total) {
+					hc0 += w[u] & 0xffffu;
+					hc1 += w[u] >> 16;
+					if (++in_call == a.splits) {        /* all slices of this call summed */
+						hv.x = rise_decay(hv.x, hc0, sh_lut, dirty);
+						hv.y = rise_decay(hv.y, hc1, sh_lut, dirty);
+						hc0 = hc1 = 0;
+						in_call = 0;
+					}
 				}
-			}
-#pragma unroll
-			for (int g = 0; g < UPD_GROUP; g++)
-				de[g] = __ldg(&a.lut[hc[g]]);
-#pragma unroll
-			for (int g = 0; g < UPD_GROUP; g++) {
-				if (c0 + g >= a.n_calls)
-					break;
-				if (hv <= 0.01f && hc[g] == 0)          /* display.cl:237-238 */
-					continue;
-				hv = __fadd_rn(__fmul_rn(__fsub_rn(hv, de[g].x), de[g].y), de[g].x);   /* :247 */
-				hv = fminf(fmaxf(hv, 0.0f), 1.0f);                                      /* :250 */
-				dirty = true;
 			}
 		}
 		if (dirty)
-			a.hist[cell] = hv;
+			*reinterpret_cast<float2 *>(a.hist + cell) = hv;
 		return;
 	}
 

@@ -52,7 +52,12 @@ struct fosphor_cu {
 	int sm_count = 0;
 
 	cudaStream_t own_stream = nullptr;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr;       /* FFT kernel, copies to the host, everything the caller orders against */
+	cudaStream_t acc_stream = nullptr;   /* count / update kernels: overlap the next chunk's FFT */
+	cudaEvent_t fft_done[2] = {nullptr, nullptr};   /* ping-pong per chunk */
+	cudaEvent_t cnt_done[2] = {nullptr, nullptr};
+	cudaEvent_t acc_done = nullptr;
+	int overlap = 1;                     /* env FOSPHOR_B200_OVERLAP=0 puts everything on one stream */
 
 	float *d_win = nullptr;
 	float2 *d_tw = nullptr;
@@ -121,7 +126,7 @@ int fail(fosphor_cu *e, int rc, const char *fmt, ...)
 
 /* ---- optional kernel timing ------------------------------------------------ */
 
-void prof_mark(fosphor_cu *e, int kernel, int end)
+void prof_mark(fosphor_cu *e, int kernel, int end, cudaStream_t st = nullptr)
 {
 	if (!e->profiling)
 		return;
@@ -133,7 +138,7 @@ void prof_mark(fosphor_cu *e, int kernel, int end)
 			return;
 		v.push_back(ev);
 	}
-	cudaEventRecord(v[i], e->stream);
+	cudaEventRecord(v[i], st ? st : e->stream);
 	if (end)
 		e->prof_used[kernel]++;
 }
@@ -302,13 +307,9 @@ void choose_slicing(const fosphor_cu *e, int n_calls, int batch, int *splits, in
 }
 
 /* fold n_calls calls (rows wf_pos .. wf_pos + n_calls*batch of the ring) into the state */
-int launch_accumulate(fosphor_cu *e, int wf_pos, int n_calls, int batch)
+int launch_accumulate(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cudaEvent_t count_done,
+                      int wf_pos, int n_calls, int batch)
 {
-	BatchTables *t;
-	int rc = get_tables(e, batch, &t);
-	if (rc)
-		return rc;
-
 	AccumArgs a;
 	a.wf = e->d_wf;
 	a.hist = e->d_hist;
@@ -334,15 +335,19 @@ int launch_accumulate(fosphor_cu *e, int wf_pos, int n_calls, int batch)
 
 	const dim3 grid(e->p.fft_len / ACC_COLS, n_calls * a.splits);
 	const size_t smem = sizeof(unsigned) * 32 * (size_t)e->p.n_bins;
-	prof_mark(e, 1, 0);
-	count_kernel<<<grid, ACC_THREADS, smem, e->stream>>>(a);
-	prof_mark(e, 1, 1);
+	prof_mark(e, 1, 0, st);
+	count_kernel<<<grid, ACC_THREADS, smem, st>>>(a);
+	prof_mark(e, 1, 1, st);
+	if (count_done)
+		CU_CHECK(e, cudaEventRecord(count_done, st));   /* the ring rows of this chunk are free again */
 	const size_t cells = (size_t)e->p.n_bins * e->p.fft_len;
-	const int cell_blocks = (int)((cells + UPD_THREADS - 1) / UPD_THREADS);
+	const size_t per_block = (size_t)UPD_THREADS * UPD_CELLS;
+	const int cell_blocks = (int)((cells + per_block - 1) / per_block);
 	const int col_blocks = (e->p.fft_len + UPD_THREADS - 1) / UPD_THREADS;
-	prof_mark(e, 2, 0);
-	update_kernel<<<cell_blocks + col_blocks, UPD_THREADS, 0, e->stream>>>(a, cell_blocks);
-	prof_mark(e, 2, 1);
+	const size_t lut_smem = sizeof(float2) * (size_t)(batch + 1);
+	prof_mark(e, 2, 0, st);
+	update_kernel<<<cell_blocks + col_blocks, UPD_THREADS, lut_smem, st>>>(a, cell_blocks);
+	prof_mark(e, 2, 1, st);
 	e->launches += 2;
 	CU_CHECK(e, cudaGetLastError());
 	return 0;
@@ -380,18 +385,42 @@ int process_device_calls(fosphor_cu *e, const float2 *in, int n_calls, int batch
 		if (rc)
 			return rc;
 	}
-	if (batch > 0) {
-		/* a chunk = calls whose rows fit the ring and whose slices fit the count buffer */
-		int calls_per_chunk = e->p.wf_rows / batch;          /* >= 1: wf_rows >= batch_max */
+	if (batch > 0 && n_calls > 0) {
+		BatchTables *t;
+		int rc = get_tables(e, batch, &t);       /* uploads (if new) are ordered before the first FFT */
+		if (rc)
+			return rc;
+		/* A chunk = calls folded by one FFT + count + update launch triple.  Its rows
+		 * must fit the ring and its slices the count buffer; with room for two chunks
+		 * in the ring the count/update of chunk c (acc_stream) overlap the FFT of
+		 * chunk c+1 (main stream). */
+		const int ring_calls = e->p.wf_rows / batch;         /* >= 1: wf_rows >= batch_max */
+		int calls_per_chunk = ring_calls;
+		const bool two_streams = e->overlap && ring_calls >= 2 && n_calls > ring_calls / 2;
+		if (two_streams)
+			calls_per_chunk = ring_calls / 2;
 		if (calls_per_chunk > e->max_slices)
 			calls_per_chunk = e->max_slices;
-		for (int c0 = 0; c0 < n_calls; c0 += calls_per_chunk) {
+		cudaStream_t acc = two_streams ? e->acc_stream : e->stream;
+		int chunk = 0;
+		for (int c0 = 0; c0 < n_calls; c0 += calls_per_chunk, chunk++) {
 			const int nc = n_calls - c0 < calls_per_chunk ? n_calls - c0 : calls_per_chunk;
+			const int pp = chunk & 1;
+			if (two_streams && chunk >= 2)       /* rows about to be overwritten were read by count(chunk-2) */
+				CU_CHECK(e, cudaStreamWaitEvent(e->stream, e->cnt_done[pp], 0));
 			CU_CHECK(e, launch_fft(e, in + (long long)c0 * batch * hop, hop, e->wf_pos, nc * batch));
-			int rc = launch_accumulate(e, e->wf_pos, nc, batch);
+			if (two_streams) {
+				CU_CHECK(e, cudaEventRecord(e->fft_done[pp], e->stream));
+				CU_CHECK(e, cudaStreamWaitEvent(acc, e->fft_done[pp], 0));
+			}
+			rc = launch_accumulate(e, t, acc, two_streams ? e->cnt_done[pp] : nullptr, e->wf_pos, nc, batch);
 			if (rc)
 				return rc;
 			e->wf_pos = (e->wf_pos + nc * batch) & (e->p.wf_rows - 1);   /* cl.c:954, nc times */
+		}
+		if (two_streams) {                       /* join: the caller's stream sees the finished state */
+			CU_CHECK(e, cudaEventRecord(e->acc_done, acc));
+			CU_CHECK(e, cudaStreamWaitEvent(e->stream, e->acc_done, 0));
 		}
 	}
 	e->state = ST_PENDING;                /* cl.c:957 */
@@ -493,6 +522,12 @@ void fosphor_cu_destroy(struct fosphor_cu *e)
 		for (int j = 0; j < 2; j++)
 			for (cudaEvent_t ev : e->prof_ev[k][j])
 				cudaEventDestroy(ev);
+	if (e->acc_stream) { cudaStreamSynchronize(e->acc_stream); cudaStreamDestroy(e->acc_stream); }
+	for (int i = 0; i < 2; i++) {
+		if (e->fft_done[i]) cudaEventDestroy(e->fft_done[i]);
+		if (e->cnt_done[i]) cudaEventDestroy(e->cnt_done[i]);
+	}
+	if (e->acc_done) cudaEventDestroy(e->acc_done);
 	if (e->own_stream) cudaStreamDestroy(e->own_stream);
 	delete e;
 }
@@ -546,6 +581,14 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 	e->sm_count = prop.multiProcessorCount;
 	CREATE_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
 	e->stream = e->own_stream;
+	CREATE_CHECK(cudaStreamCreateWithFlags(&e->acc_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) {
+		CREATE_CHECK(cudaEventCreateWithFlags(&e->fft_done[i], cudaEventDisableTiming));
+		CREATE_CHECK(cudaEventCreateWithFlags(&e->cnt_done[i], cudaEventDisableTiming));
+	}
+	CREATE_CHECK(cudaEventCreateWithFlags(&e->acc_done, cudaEventDisableTiming));
+	if (const char *v = getenv("FOSPHOR_B200_OVERLAP"))
+		e->overlap = atoi(v);
 
 	const size_t n = p.fft_len, k = p.n_bins, w = p.wf_rows;
 	CREATE_CHECK(cudaMalloc(&e->d_win, sizeof(float) * n));
@@ -595,6 +638,8 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 		if (const char *v = getenv("FOSPHOR_B200_FFT_VARIANT"))
 			e->fft_variant = atoi(v);
 	}
+	CREATE_CHECK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                                  (int)(sizeof(float2) * (size_t)(p.batch_max + 1))));
 	CREATE_CHECK(cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                                  (int)(sizeof(unsigned) * 32 * k)));
 
