@@ -35,6 +35,7 @@
  */
 #pragma once
 #include <cfloat>
+#include <cuda.h>            /* CUtensorMap (types only; the encoder is fetched at run time) */
 #include <cuda_runtime.h>
 
 namespace fosphor_b200 {
@@ -187,8 +188,168 @@ count_kernel(const AccumArgs a)
 		dst[(size_t)bin * N] = (unsigned short)sh_hits[bin * 32 + lane];
 }
 
+/* ---- TMA-staged variant of count_kernel ----------------------------------- */
+/*
+ * The plain kernel above is latency bound: ncu shows ~16 long-scoreboard stall
+ * cycles per issue, the compiler sinks the row loads next to their uses and a
+ * warp ends up with 3-4 loads in flight.  Here one elected thread asks the TMA
+ * engine for whole row blocks - a 2-D tensor-map copy of 16 rows x 32 columns
+ * (2 KB) per instruction, 8 per 128-row block - into a double-buffered
+ * shared-memory stage, completion on an mbarrier; all 8 warps then count from
+ * shared memory (lane == column, conflict free) while the next block is in
+ * flight.  Same arithmetic, same canonical summation order, bit-identical
+ * results.  Needs ring position and batch to be multiples of TMA_ROWS.
+ */
+constexpr int TMA_ROWS = 16;          /* rows per tensor-map box */
+
+__device__ __forceinline__ unsigned cnt_smem_u32(const void *p)
+{
+	return (unsigned)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *tmap, int c0, int c1, unsigned bar)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+	             ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+struct __align__(128) CountStage {
+	float rows[2][ROWBLOCK][32];          /* 2 x 16 KB, TMA destinations (128-byte rows) */
+	float wts[2][ROWBLOCK];
+	unsigned long long bar[2];
+	float live[ACC_WARPS][32];
+	float mx[ACC_WARPS][32];
+};
+
+__global__ void __launch_bounds__(ACC_THREADS)
+count_tma_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
+{
+	extern __shared__ __align__(128) unsigned char cnt_smem[];
+	CountStage &st = *reinterpret_cast<CountStage *>(cnt_smem);
+	unsigned *sh_hits = reinterpret_cast<unsigned *>(cnt_smem + sizeof(CountStage));   /* [K][32] */
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int tile = blockIdx.x, slice = blockIdx.y;
+	const int call = slice / a.splits, split = slice - call * a.splits;
+	const int col = tile * ACC_COLS + lane;
+	const int K = a.n_bins, N = a.n;
+
+	const int row0 = split * a.rows_per_split;
+	const int row1 = min(a.batch, row0 + a.rows_per_split);
+	const int nblocks = (row1 - row0 + ROWBLOCK - 1) / ROWBLOCK;
+	const unsigned ring0 = (unsigned)(a.wf_pos + call * a.batch);
+	const unsigned mask = (unsigned)a.wf_mask;
+	const unsigned bar0 = cnt_smem_u32(&st.bar[0]);
+
+	auto issue = [&](int blk) {          /* thread 0 only */
+		const int b0 = row0 + blk * ROWBLOCK;
+		const int nrows = min(ROWBLOCK, row1 - b0);
+		const unsigned bar = bar0 + 8u * (unsigned)(blk & 1);
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+		             ::"r"(bar), "r"((unsigned)(nrows * 32 * sizeof(float))) : "memory");
+		for (int r = 0; r < nrows; r += TMA_ROWS)
+			tma_load_2d(cnt_smem_u32(&st.rows[blk & 1][r][0]), &tmap, tile * ACC_COLS,
+			            (int)((ring0 + (unsigned)(b0 + r)) & mask), bar);
+	};
+
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		issue(0);
+		if (nblocks > 1)
+			issue(1);
+	}
+	{
+		uint4 *z = reinterpret_cast<uint4 *>(sh_hits);
+		for (int i = threadIdx.x; i < K * 8; i += ACC_THREADS)
+			z[i] = make_uint4(0u, 0u, 0u, 0u);
+	}
+	/* live weights of the first two blocks */
+	for (int i = threadIdx.x; i < 2 * ROWBLOCK; i += ACC_THREADS) {
+		const int s = row0 + i;
+		if (s < row1)
+			st.wts[(i / ROWBLOCK) & 1][i % ROWBLOCK] = __ldg(&a.weights[s]);
+	}
+	__syncthreads();
+
+	const float kmaxf = (float)(K - 1);
+	unsigned *my_hits = sh_hits + lane;
+	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
+	const size_t part_base = (size_t)call * blocks_per_call + (size_t)(row0 / ROWBLOCK);
+	unsigned phases = 0u;
+
+	for (int blk = 0; blk < nblocks; blk++) {
+		const int buf = blk & 1;
+		const int b0 = row0 + blk * ROWBLOCK;
+		const int nrows = min(ROWBLOCK, row1 - b0);
+
+		/* wait for the TMA data of this block */
+		{
+			const unsigned bar = bar0 + 8u * (unsigned)buf;
+			const unsigned parity = (phases >> buf) & 1u;
+			unsigned ok;
+			do {
+				asm volatile("{\n\t.reg .pred p;\n\t"
+				             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+				             "selp.u32 %0, 1, 0, p;\n\t}"
+				             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+			} while (!ok);
+			phases ^= 1u << buf;
+		}
+
+		float live = 0.0f, mx = -1000.0f;               /* display.cl:91,113 */
+		const float *rp = &st.rows[buf][warp][lane];
+		const float *wp = &st.wts[buf][warp];
+#pragma unroll 4
+		for (int r = warp; r < nrows; r += ACC_WARPS) {
+			const float pw = *rp;
+			live = fmaf(pw, *wp, live);                                   /* display.cl:149-150 */
+			mx = fmaxf(mx, pw);                                           /* :139 */
+			const int bin = map_bin(__fmul_rn(a.hscale, __fadd_rn(pw, a.hofs)), kmaxf);
+			atomicAdd(my_hits + bin * 32, 1u);                            /* :170-177 */
+			rp += ACC_WARPS * 32;
+			wp += ACC_WARPS;
+		}
+		st.live[warp][lane] = live;
+		st.mx[warp][lane] = mx;
+		__syncthreads();                                 /* stage buffer `buf` fully consumed */
+
+		if (warp == 0) {
+			float sum = 0.0f, m = -1000.0f;
+#pragma unroll
+			for (int w = 0; w < ACC_WARPS; w++) {
+				sum += st.live[w][lane];
+				m = fmaxf(m, st.mx[w][lane]);
+			}
+			const size_t o = (part_base + (size_t)blk) * N + col;
+			a.part_live[o] = sum;
+			a.part_max[o] = m;
+		}
+		if (blk + 2 < nblocks) {
+			if (threadIdx.x == 0) {
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				issue(blk + 2);
+			}
+			for (int i = threadIdx.x; i < ROWBLOCK; i += ACC_THREADS) {
+				const int s = b0 + 2 * ROWBLOCK + i;
+				if (s < row1)
+					st.wts[buf][i] = __ldg(&a.weights[s]);
+			}
+		}
+		__syncthreads();                                 /* live/mx scratch + weights ready */
+	}
+
+	unsigned short *dst = a.cnt + (size_t)slice * K * N + col;
+#pragma unroll 4
+	for (int bin = warp; bin < K; bin += ACC_WARPS)
+		dst[(size_t)bin * N] = (unsigned short)sh_hits[bin * 32 + lane];
+}
+
 constexpr int UPD_CELLS = 2;      /* adjacent cells per thread (one 32-bit load of two u16 counts) */
 constexpr int UPD_SLICES = 8;     /* slices whose loads are issued together */
+constexpr int UPD_COLS = 32;      /* columns per live/max-hold block */
 
 __device__ __forceinline__ float rise_decay(float hv, unsigned hc, const float2 *lut, bool &dirty)
 {
@@ -202,7 +363,7 @@ __device__ __forceinline__ float rise_decay(float hv, unsigned hc, const float2 
 
 /* blocks [0, cell_blocks): one thread per UPD_CELLS adjacent histogram cells
  * (bin-major: a warp covers 64 consecutive columns of one bin); blocks beyond:
- * one thread per column for live / max-hold.  N is even, so a cell pair never
+ * UPD_COLS columns each for live / max-hold.  N is even, so a cell pair never
  * straddles two bins. */
 __global__ void __launch_bounds__(UPD_THREADS)
 update_kernel(const AccumArgs a, int cell_blocks)
@@ -249,21 +410,36 @@ update_kernel(const AccumArgs a, int cell_blocks)
 		return;
 	}
 
-	const int col = ((int)blockIdx.x - cell_blocks) * UPD_THREADS + threadIdx.x;
-	if (col >= N)
+	/* ---- live / max-hold: a block owns UPD_COLS columns.  All partials of the
+	 * chunk are fetched in parallel into shared memory first (the loads are
+	 * independent); then one thread per column runs the serial recurrences. ---- */
+	float *sh_part = reinterpret_cast<float *>(sh_lut);       /* [2][nparts][UPD_COLS] */
+	const int col0 = ((int)blockIdx.x - cell_blocks) * UPD_COLS;
+	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
+	const int nparts = a.n_calls * blocks_per_call;
+	for (int i = threadIdx.x; i < nparts * UPD_COLS; i += UPD_THREADS) {
+		const int p = i / UPD_COLS, c = i % UPD_COLS;
+		if (col0 + c < N) {
+			sh_part[i] = __ldcg(&a.part_live[(size_t)p * N + col0 + c]);
+			sh_part[nparts * UPD_COLS + i] = __ldcg(&a.part_max[(size_t)p * N + col0 + c]);
+		}
+	}
+	__syncthreads();
+	const int col = col0 + threadIdx.x;
+	if (threadIdx.x >= UPD_COLS || col >= N)
 		return;
 	const int half = N >> 1;
 	const int i = col ^ half;                                 /* display.cl:201 */
 	const float xpos = ((float)i / (float)half) - 1.0f;       /* :209 */
 	float y = a.spectrum[i].y;
 	float m = a.spectrum[N + i].y;
-	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
+	const float *pl = sh_part + threadIdx.x;
+	const float *pm = sh_part + nparts * UPD_COLS + threadIdx.x;
 	for (int c = 0; c < a.n_calls; c++) {
 		float sum = 0.0f, bmax = -1000.0f;
 		for (int b = 0; b < blocks_per_call; b++) {
-			const size_t o = (size_t)(c * blocks_per_call + b) * N + col;
-			sum += __ldcg(&a.part_live[o]);
-			bmax = fmaxf(bmax, __ldcg(&a.part_max[o]));
+			sum += pl[(c * blocks_per_call + b) * UPD_COLS];
+			bmax = fmaxf(bmax, pm[(c * blocks_per_call + b) * UPD_COLS]);
 		}
 		/* live spectrum, display.cl:203-214 */
 		if (!isfinite(y))

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/fosphor_b200.h"
@@ -31,7 +32,8 @@ enum { ST_BOOTING = 0, ST_PENDING, ST_READY };   /* cl.c:95-99 */
 
 constexpr int N_TABLES = 8;      /* cached (weights, lut) sets, one per distinct batch size */
 constexpr int MAX_SLICES = 128;  /* (call, row-split) slices folded by one count/update launch pair */
-constexpr size_t CNT_BUDGET = (size_t)1 << 30;   /* bytes of u16 hit-count slices kept on the device */
+constexpr size_t CNT_BUDGET = (size_t)1 << 30;
+constexpr size_t UPD_SMEM_MAX = 96 * 1024;   /* dynamic shared memory of update_kernel */   /* bytes of u16 hit-count slices kept on the device */
 
 struct BatchTables {
 	int batch = -1;
@@ -58,6 +60,10 @@ struct fosphor_cu {
 	cudaEvent_t cnt_done[2] = {nullptr, nullptr};
 	cudaEvent_t acc_done = nullptr;
 	int overlap = 1;                     /* env FOSPHOR_B200_OVERLAP=0 puts everything on one stream */
+	CUtensorMap wf_tmap;                 /* waterfall ring as a 2-D tensor, box = 16 rows x 32 columns */
+	bool tmap_ok = false;
+	int count_variant = 1;               /* 1: TMA-staged count kernel where applicable, 0: plain
+	                                      * (env FOSPHOR_B200_COUNT_VARIANT) */
 
 	float *d_win = nullptr;
 	float2 *d_tw = nullptr;
@@ -335,16 +341,27 @@ int launch_accumulate(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cuda
 
 	const dim3 grid(e->p.fft_len / ACC_COLS, n_calls * a.splits);
 	const size_t smem = sizeof(unsigned) * 32 * (size_t)e->p.n_bins;
+	const bool use_tma = e->tmap_ok && e->count_variant != 0 &&
+	                     (batch % TMA_ROWS) == 0 && (wf_pos % TMA_ROWS) == 0;
 	prof_mark(e, 1, 0, st);
-	count_kernel<<<grid, ACC_THREADS, smem, st>>>(a);
+	if (use_tma)
+		count_tma_kernel<<<grid, ACC_THREADS, smem + sizeof(CountStage), st>>>(a, e->wf_tmap);
+	else
+		count_kernel<<<grid, ACC_THREADS, smem, st>>>(a);
 	prof_mark(e, 1, 1, st);
 	if (count_done)
 		CU_CHECK(e, cudaEventRecord(count_done, st));   /* the ring rows of this chunk are free again */
 	const size_t cells = (size_t)e->p.n_bins * e->p.fft_len;
 	const size_t per_block = (size_t)UPD_THREADS * UPD_CELLS;
 	const int cell_blocks = (int)((cells + per_block - 1) / per_block);
-	const int col_blocks = (e->p.fft_len + UPD_THREADS - 1) / UPD_THREADS;
-	const size_t lut_smem = sizeof(float2) * (size_t)(batch + 1);
+	const int col_blocks = (e->p.fft_len + UPD_COLS - 1) / UPD_COLS;
+	size_t lut_smem = sizeof(float2) * (size_t)(batch + 1);
+	{
+		const size_t parts = (size_t)n_calls * ((batch + ROWBLOCK - 1) / ROWBLOCK);
+		const size_t part_smem = sizeof(float) * 2 * parts * UPD_COLS;
+		if (part_smem > lut_smem)
+			lut_smem = part_smem;
+	}
 	prof_mark(e, 2, 0, st);
 	update_kernel<<<cell_blocks + col_blocks, UPD_THREADS, lut_smem, st>>>(a, cell_blocks);
 	prof_mark(e, 2, 1, st);
@@ -401,6 +418,13 @@ int process_device_calls(fosphor_cu *e, const float2 *in, int n_calls, int batch
 			calls_per_chunk = ring_calls / 2;
 		if (calls_per_chunk > e->max_slices)
 			calls_per_chunk = e->max_slices;
+		{
+			/* the live/max partials of a chunk are staged in shared memory by update_kernel */
+			const int max_parts = (int)(UPD_SMEM_MAX / (sizeof(float) * 2 * UPD_COLS));
+			const int by_parts = max_parts / ((batch + ROWBLOCK - 1) / ROWBLOCK);
+			if (calls_per_chunk > by_parts)
+				calls_per_chunk = by_parts > 0 ? by_parts : 1;
+		}
 		cudaStream_t acc = two_streams ? e->acc_stream : e->stream;
 		int chunk = 0;
 		for (int c0 = 0; c0 < n_calls; c0 += calls_per_chunk, chunk++) {
@@ -638,8 +662,41 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 		if (const char *v = getenv("FOSPHOR_B200_FFT_VARIANT"))
 			e->fft_variant = atoi(v);
 	}
-	CREATE_CHECK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                                  (int)(sizeof(float2) * (size_t)(p.batch_max + 1))));
+	{
+		size_t upd = sizeof(float2) * (size_t)(p.batch_max + 1);
+		if (upd < UPD_SMEM_MAX)
+			upd = UPD_SMEM_MAX;
+		CREATE_CHECK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd));
+	}
+	CREATE_CHECK(cudaFuncSetAttribute(count_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                                  (int)(sizeof(unsigned) * 32 * k + sizeof(CountStage))));
+	if (const char *v = getenv("FOSPHOR_B200_COUNT_VARIANT"))
+		e->count_variant = atoi(v);
+	{
+		/* 2-D tensor map over the waterfall ring for the TMA-staged count kernel; the
+		 * encoder lives in the driver and is fetched through the runtime */
+		typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+		                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+		                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+		                              CUtensorMapFloatOOBfill);
+		void *fn = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+		    qres == cudaDriverEntryPointSuccess && fn) {
+			const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)w};
+			const cuuint64_t gstride[1] = {(cuuint64_t)n * sizeof(float)};
+			const cuuint32_t box[2] = {ACC_COLS, TMA_ROWS};
+			const cuuint32_t estr[2] = {1, 1};
+			CUresult cr = reinterpret_cast<encode_fn>(fn)(&e->wf_tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, e->d_wf,
+				gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+				CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+			e->tmap_ok = (cr == CUDA_SUCCESS) && (w % TMA_ROWS) == 0;
+		} else {
+			cudaGetLastError();
+		}
+		if (!e->tmap_ok)
+			fprintf(stderr, "[w] fosphor_b200: tensor-map encode unavailable, using the plain count kernel\n");
+	}
 	CREATE_CHECK(cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                                  (int)(sizeof(unsigned) * 32 * k)));
 

@@ -221,23 +221,28 @@ def test_validation_and_state_machine(torch_cuda):
     eng.close()
 
 
-def test_stream_kernel_equals_plain_kernel(torch_cuda, monkeypatch):
-    """The TMA-prefetching persistent FFT kernel and the plain one do the same
-    arithmetic: bit-identical waterfall / histogram / spectrum (N = 1024 and 512)."""
+def test_kernel_variants_are_bit_identical(torch_cuda, monkeypatch):
+    """TMA-prefetching FFT kernel vs plain, TMA-staged count kernel vs plain,
+    two-stream overlap vs one stream: same arithmetic, bit-identical waterfall /
+    histogram / spectrum (N = 1024 and 512, several calls folded per launch)."""
     torch = torch_cuda
     for n in (1024, 512):
-        x = signals.noise_tones(n * 1024, n_fft=n, seed=77)
+        calls, b = 5, 1024
+        x = signals.noise_tones(n * b * calls, n_fft=n, seed=77)
         d = _to_dev(torch, x)
         outs = []
-        for variant in ("1", "0"):
-            monkeypatch.setenv("FOSPHOR_B200_FFT_VARIANT", variant)
-            e = _engine(fft_len=n, n_bins=256)
-            assert e.process_device(d.data_ptr(), 1024) == 0
+        for fftv, cntv, ov in (("1", "1", "1"), ("0", "0", "0"), ("1", "0", "1"), ("0", "1", "0")):
+            monkeypatch.setenv("FOSPHOR_B200_FFT_VARIANT", fftv)
+            monkeypatch.setenv("FOSPHOR_B200_COUNT_VARIANT", cntv)
+            monkeypatch.setenv("FOSPHOR_B200_OVERLAP", ov)
+            e = _engine(fft_len=n, n_bins=256, wf_rows=4096)
+            assert e.process_device_multi(d.data_ptr(), calls, b) == 0
             _, h = e.finish()
             outs.append({k: v.copy() for k, v in h.items()})
             e.close()
-        for key in ("waterfall", "histogram", "spectrum"):
-            assert np.array_equal(outs[0][key], outs[1][key]), (n, key)
+        for o in outs[1:]:
+            for key in ("waterfall", "histogram", "spectrum"):
+                assert np.array_equal(outs[0][key], o[key]), (n, key)
 
 
 # ---------------------------------------------------------------------------
