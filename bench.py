@@ -258,9 +258,13 @@ def run_b200(args):
             traffic = json.load(f).get("dram_bytes_per_launch")
 
     # the same kernels timed without the count/update overlap (one stream), for reference
+    old_ov = os.environ.get("FOSPHOR_B200_OVERLAP")
     os.environ["FOSPHOR_B200_OVERLAP"] = "0"
     eng_iso = Fosphor(fft_len=n, n_bins=k, wf_rows=wf_rows, device=local, stream=stream.cuda_stream)
-    os.environ.pop("FOSPHOR_B200_OVERLAP")
+    if old_ov is None:
+        os.environ.pop("FOSPHOR_B200_OVERLAP")
+    else:
+        os.environ["FOSPHOR_B200_OVERLAP"] = old_ov
     eng, eng_iso = eng_iso, eng
     ms_iso = timed(lambda i: step_device(i, True), prof_steps, 2)
     eng.profile(True)

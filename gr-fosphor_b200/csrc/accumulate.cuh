@@ -65,56 +65,60 @@ struct AccumArgs {
 	float mh_keep, mh_mix;    /* display.cl:303 */
 };
 
-__device__ __forceinline__ int map_bin(float x, float kmaxf)
+__device__ __forceinline__ int map_bin(float x, int kmax)
 {
 	/* display.cl:161-165: (int)round(x), half away from zero, clamped to
-	 * [0, K-1].  Clamping first is equivalent and makes the special values
-	 * explicit: NaN and -inf -> 0 (fmaxf drops the NaN), +inf -> K-1 - what the
-	 * reference yields on the NVIDIA OpenCL runtime; the rule is fixed in
-	 * DESIGN.md.  For x >= 0, round-half-away = rint(x) bumped on exact ties. */
-	x = fminf(fmaxf(x, 0.0f), kmaxf);
+	 * [0, K-1].  rint() + a bump on exact .5 ties is round-half-away for x >= 0
+	 * (negative x clamp to 0 either way); the float->int conversion saturates,
+	 * so NaN -> 0, -inf -> 0, +inf -> K-1: what the reference yields on the
+	 * NVIDIA OpenCL runtime (golden case zeros_then_data), fixed as the rule in
+	 * DESIGN.md. */
 	float r = rintf(x);
 	if (x - r == 0.5f)
 		r += 1.0f;
-	return (int)r;
+	return min(max(__float2int_rz(r), 0), kmax);
 }
 
 constexpr int ROWBLOCK = 128;     /* canonical unit of the f32 live partial sums */
 constexpr int BLK_GROUP = 8;      /* row blocks reduced per pass through shared memory */
+
+constexpr int WARP_ROWS = ROWBLOCK / ACC_WARPS;   /* 16 consecutive rows of a block per warp */
 
 struct RowCtx {
 	const float *base;        /* wf + column */
 	const float *weights;
 	unsigned *my_hits;        /* sh_hits + lane */
 	unsigned ring0, mask, n;
-	float hscale, hofs, kmaxf;
+	float hscale, hofs;
+	int kmax;
 };
 
-/* U rows (s, s+8, ..., one per CTA-wide stride) of one column per lane: all
- * loads first, then the arithmetic; no bounds checks inside. */
+/* U consecutive rows s .. s+U-1 of one column per lane: all loads first, then
+ * the arithmetic; no bounds checks inside. */
 template <int U>
 __device__ __forceinline__ void count_rows(const RowCtx &c, int s, float &live, float &mx)
 {
 	float pw[U], wt[U];
 #pragma unroll
 	for (int u = 0; u < U; u++) {
-		const unsigned r = (c.ring0 + (unsigned)(s + u * ACC_WARPS)) & c.mask;
+		const unsigned r = (c.ring0 + (unsigned)(s + u)) & c.mask;
 		pw[u] = __ldcg(c.base + (size_t)(r * c.n));
-		wt[u] = __ldg(c.weights + s + u * ACC_WARPS);
+		wt[u] = __ldg(c.weights + s + u);
 	}
 #pragma unroll
 	for (int u = 0; u < U; u++) {
 		live = fmaf(pw[u], wt[u], live);                                  /* display.cl:149-150 */
 		mx = fmaxf(mx, pw[u]);                                            /* :139 */
-		const int bin = map_bin(__fmul_rn(c.hscale, __fadd_rn(pw[u], c.hofs)), c.kmaxf);
+		const int bin = map_bin(__fmul_rn(c.hscale, __fadd_rn(pw[u], c.hofs)), c.kmax);
 		atomicAdd(c.my_hits + bin * 32, 1u);                              /* :170-177 */
 	}
 }
 
 /* The f32 live-spectrum partial sums are formed per ROWBLOCK rows in a fixed
- * order (warp w takes rows w, w+8, ... of the block; the 8 warp partials are
- * added in warp order; update_kernel adds the blocks in row order), so the
- * result does not depend on how a call is cut into slices. */
+ * order (warp w takes rows 16w .. 16w+15 of the block in row order; the 8 warp
+ * partials are added in warp order; update_kernel adds the blocks in row
+ * order), so the result does not depend on how a call is cut into slices nor
+ * on which of the two count kernels ran. */
 __global__ void __launch_bounds__(ACC_THREADS)
 count_kernel(const AccumArgs a)
 {
@@ -147,7 +151,7 @@ count_kernel(const AccumArgs a)
 	c.n = (unsigned)N;
 	c.hscale = a.hscale;
 	c.hofs = a.hofs;
-	c.kmaxf = (float)(K - 1);
+	c.kmax = K - 1;
 	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
 	const size_t part_base = (size_t)call * blocks_per_call;
 
@@ -157,12 +161,13 @@ count_kernel(const AccumArgs a)
 		for (int b0 = g0; b0 < g1; b0 += ROWBLOCK, nblk++) {
 			const int b1 = min(g1, b0 + ROWBLOCK);
 			float live = 0.0f, mx = -1000.0f;       /* display.cl:91,113 */
-			int s = b0 + warp;
-			for (; s + 7 * ACC_WARPS < b1; s += 8 * ACC_WARPS)
+			int s = b0 + warp * WARP_ROWS;
+			const int e = min(b1, s + WARP_ROWS);
+			for (; s + 8 <= e; s += 8)
 				count_rows<8>(c, s, live, mx);
-			for (; s + ACC_WARPS < b1; s += 2 * ACC_WARPS)
+			for (; s + 2 <= e; s += 2)
 				count_rows<2>(c, s, live, mx);
-			if (s < b1)
+			if (s < e)
 				count_rows<1>(c, s, live, mx);
 			sh_live[nblk][warp][lane] = live;
 			sh_max[nblk][warp][lane] = mx;
@@ -190,17 +195,21 @@ count_kernel(const AccumArgs a)
 
 /* ---- TMA-staged variant of count_kernel ----------------------------------- */
 /*
- * The plain kernel above is latency bound: ncu shows ~16 long-scoreboard stall
- * cycles per issue, the compiler sinks the row loads next to their uses and a
- * warp ends up with 3-4 loads in flight.  Here one elected thread asks the TMA
- * engine for whole row blocks - a 2-D tensor-map copy of 16 rows x 32 columns
- * (2 KB) per instruction, 8 per 128-row block - into a double-buffered
- * shared-memory stage, completion on an mbarrier; all 8 warps then count from
- * shared memory (lane == column, conflict free) while the next block is in
- * flight.  Same arithmetic, same canonical summation order, bit-identical
- * results.  Needs ring position and batch to be multiples of TMA_ROWS.
+ * The plain kernel above is latency bound (ncu: ~16 long-scoreboard stall cycles
+ * per issue; the compiler sinks the row loads next to their uses and a warp ends
+ * up with 3-4 loads in flight).  Here every warp runs its own little pipeline:
+ * its 16 rows x 32 columns of a row block are exactly one 2-D tensor-map box
+ * (2 KB), which lane 0 requests from the TMA engine TMA_DEPTH blocks ahead into
+ * a private shared-memory ring, completion on the warp's own mbarriers.  The
+ * rows are then counted from shared memory (lane == column, conflict free).
+ * No block-wide barrier inside the loop, no global load instruction except the
+ * 16 weights per block.  Same arithmetic and the same canonical summation order
+ * as count_kernel: bit-identical results.  Needs ring position and batch to be
+ * multiples of 16 rows.
  */
-constexpr int TMA_ROWS = 16;          /* rows per tensor-map box */
+constexpr int TMA_ROWS = WARP_ROWS;   /* rows per tensor-map box == rows per warp per block */
+constexpr int TMA_DEPTH = 2;          /* boxes per warp: one being counted, one in flight */
+static_assert(TMA_ROWS == 16, "box is 16 rows x 32 columns");
 
 __device__ __forceinline__ unsigned cnt_smem_u32(const void *p)
 {
@@ -213,12 +222,13 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *tma
 	             ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
+constexpr int CNT_MAXBLK = 4;         /* row blocks whose partials are kept before a flush */
+
 struct __align__(128) CountStage {
-	float rows[2][ROWBLOCK][32];          /* 2 x 16 KB, TMA destinations (128-byte rows) */
-	float wts[2][ROWBLOCK];
-	unsigned long long bar[2];
-	float live[ACC_WARPS][32];
-	float mx[ACC_WARPS][32];
+	float rows[ACC_WARPS][TMA_DEPTH][TMA_ROWS][32];      /* 8 x 4 x 2 KB, TMA destinations */
+	unsigned long long bar[ACC_WARPS][TMA_DEPTH];
+	float live[CNT_MAXBLK][ACC_WARPS][32];
+	float mx[CNT_MAXBLK][ACC_WARPS][32];
 };
 
 __global__ void __launch_bounds__(ACC_THREADS)
@@ -239,106 +249,93 @@ count_tma_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 	const int nblocks = (row1 - row0 + ROWBLOCK - 1) / ROWBLOCK;
 	const unsigned ring0 = (unsigned)(a.wf_pos + call * a.batch);
 	const unsigned mask = (unsigned)a.wf_mask;
-	const unsigned bar0 = cnt_smem_u32(&st.bar[0]);
+	const unsigned bar0 = cnt_smem_u32(&st.bar[warp][0]);
+	const unsigned stage0 = cnt_smem_u32(&st.rows[warp][0][0][0]);
+	constexpr unsigned BOX_BYTES = TMA_ROWS * 32 * sizeof(float);
 
-	auto issue = [&](int blk) {          /* thread 0 only */
-		const int b0 = row0 + blk * ROWBLOCK;
-		const int nrows = min(ROWBLOCK, row1 - b0);
-		const unsigned bar = bar0 + 8u * (unsigned)(blk & 1);
-		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-		             ::"r"(bar), "r"((unsigned)(nrows * 32 * sizeof(float))) : "memory");
-		for (int r = 0; r < nrows; r += TMA_ROWS)
-			tma_load_2d(cnt_smem_u32(&st.rows[blk & 1][r][0]), &tmap, tile * ACC_COLS,
-			            (int)((ring0 + (unsigned)(b0 + r)) & mask), bar);
+	/* the box of this warp in block blk starts at row row0 + blk*128 + 16*warp */
+	auto my_rows = [&](int blk) { return row0 + blk * ROWBLOCK + warp * WARP_ROWS; };
+	auto issue = [&](int blk) {          /* lane 0 only; box present iff its first row exists */
+		const int s = my_rows(blk);
+		if (s < row1) {
+			const unsigned slot = (unsigned)(blk % TMA_DEPTH);
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+			             ::"r"(bar0 + 8u * slot), "r"(BOX_BYTES) : "memory");
+			tma_load_2d(stage0 + slot * BOX_BYTES, &tmap, tile * ACC_COLS,
+			            (int)((ring0 + (unsigned)s) & mask), bar0 + 8u * slot);
+		}
 	};
 
-	if (threadIdx.x == 0) {
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u));
+	if (lane == 0) {
+#pragma unroll
+		for (int d = 0; d < TMA_DEPTH; d++)
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * d));
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-		issue(0);
-		if (nblocks > 1)
-			issue(1);
+		for (int d = 0; d < TMA_DEPTH && d < nblocks; d++)
+			issue(d);
 	}
 	{
 		uint4 *z = reinterpret_cast<uint4 *>(sh_hits);
 		for (int i = threadIdx.x; i < K * 8; i += ACC_THREADS)
 			z[i] = make_uint4(0u, 0u, 0u, 0u);
 	}
-	/* live weights of the first two blocks */
-	for (int i = threadIdx.x; i < 2 * ROWBLOCK; i += ACC_THREADS) {
-		const int s = row0 + i;
-		if (s < row1)
-			st.wts[(i / ROWBLOCK) & 1][i % ROWBLOCK] = __ldg(&a.weights[s]);
-	}
 	__syncthreads();
 
-	const float kmaxf = (float)(K - 1);
+	const int kmax = K - 1;
 	unsigned *my_hits = sh_hits + lane;
 	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
 	const size_t part_base = (size_t)call * blocks_per_call + (size_t)(row0 / ROWBLOCK);
-	unsigned phases = 0u;
+	unsigned phases = 0u;                    /* bit d = parity to wait for on slot d */
 
-	for (int blk = 0; blk < nblocks; blk++) {
-		const int buf = blk & 1;
-		const int b0 = row0 + blk * ROWBLOCK;
-		const int nrows = min(ROWBLOCK, row1 - b0);
-
-		/* wait for the TMA data of this block */
-		{
-			const unsigned bar = bar0 + 8u * (unsigned)buf;
-			const unsigned parity = (phases >> buf) & 1u;
-			unsigned ok;
-			do {
-				asm volatile("{\n\t.reg .pred p;\n\t"
-				             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-				             "selp.u32 %0, 1, 0, p;\n\t}"
-				             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-			} while (!ok);
-			phases ^= 1u << buf;
+	for (int g0 = 0; g0 < nblocks; g0 += CNT_MAXBLK) {
+		const int g1 = min(nblocks, g0 + CNT_MAXBLK);
+		for (int blk = g0; blk < g1; blk++) {
+			const int s = my_rows(blk);
+			float live = 0.0f, mx = -1000.0f;               /* display.cl:91,113 */
+			if (s < row1) {
+				const unsigned slot = (unsigned)(blk % TMA_DEPTH);
+				const float wts = __ldg(&a.weights[s + (lane & (WARP_ROWS - 1))]);
+				unsigned ok;
+				do {
+					asm volatile("{\n\t.reg .pred p;\n\t"
+					             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+					             "selp.u32 %0, 1, 0, p;\n\t}"
+					             : "=r"(ok) : "r"(bar0 + 8u * slot), "r"((phases >> slot) & 1u) : "memory");
+				} while (!ok);
+				phases ^= 1u << slot;
+				const float *rp = &st.rows[warp][slot][0][lane];
+#pragma unroll
+				for (int r = 0; r < WARP_ROWS; r++) {
+					const float pw = rp[r * 32];
+					live = fmaf(pw, __shfl_sync(0xffffffffu, wts, r), live);      /* display.cl:149-150 */
+					mx = fmaxf(mx, pw);                                           /* :139 */
+					const int bin = map_bin(__fmul_rn(a.hscale, __fadd_rn(pw, a.hofs)), kmax);
+					atomicAdd(my_hits + bin * 32, 1u);                            /* :170-177 */
+				}
+				__syncwarp();                        /* the slot is consumed by every lane */
+				if (lane == 0 && blk + TMA_DEPTH < nblocks) {
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					issue(blk + TMA_DEPTH);
+				}
+			}
+			st.live[blk - g0][warp][lane] = live;
+			st.mx[blk - g0][warp][lane] = mx;
 		}
-
-		float live = 0.0f, mx = -1000.0f;               /* display.cl:91,113 */
-		const float *rp = &st.rows[buf][warp][lane];
-		const float *wp = &st.wts[buf][warp];
-#pragma unroll 4
-		for (int r = warp; r < nrows; r += ACC_WARPS) {
-			const float pw = *rp;
-			live = fmaf(pw, *wp, live);                                   /* display.cl:149-150 */
-			mx = fmaxf(mx, pw);                                           /* :139 */
-			const int bin = map_bin(__fmul_rn(a.hscale, __fadd_rn(pw, a.hofs)), kmaxf);
-			atomicAdd(my_hits + bin * 32, 1u);                            /* :170-177 */
-			rp += ACC_WARPS * 32;
-			wp += ACC_WARPS;
-		}
-		st.live[warp][lane] = live;
-		st.mx[warp][lane] = mx;
-		__syncthreads();                                 /* stage buffer `buf` fully consumed */
-
-		if (warp == 0) {
+		__syncthreads();
+		if (warp < g1 - g0) {
 			float sum = 0.0f, m = -1000.0f;
 #pragma unroll
 			for (int w = 0; w < ACC_WARPS; w++) {
-				sum += st.live[w][lane];
-				m = fmaxf(m, st.mx[w][lane]);
+				sum += st.live[warp][w][lane];
+				m = fmaxf(m, st.mx[warp][w][lane]);
 			}
-			const size_t o = (part_base + (size_t)blk) * N + col;
+			const size_t o = (part_base + (size_t)(g0 + warp)) * N + col;
 			a.part_live[o] = sum;
 			a.part_max[o] = m;
 		}
-		if (blk + 2 < nblocks) {
-			if (threadIdx.x == 0) {
-				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-				issue(blk + 2);
-			}
-			for (int i = threadIdx.x; i < ROWBLOCK; i += ACC_THREADS) {
-				const int s = b0 + 2 * ROWBLOCK + i;
-				if (s < row1)
-					st.wts[buf][i] = __ldg(&a.weights[s]);
-			}
-		}
-		__syncthreads();                                 /* live/mx scratch + weights ready */
+		if (g1 < nblocks)
+			__syncthreads();
 	}
 
 	unsigned short *dst = a.cnt + (size_t)slice * K * N + col;
@@ -373,24 +370,33 @@ update_kernel(const AccumArgs a, int cell_blocks)
 	const size_t KN = (size_t)K * N;
 
 	if ((int)blockIdx.x < cell_blocks) {
-		for (int i = threadIdx.x; i <= a.batch; i += UPD_THREADS)
-			sh_lut[i] = __ldg(&a.lut[i]);
-		__syncthreads();
-		const size_t cell = ((size_t)blockIdx.x * UPD_THREADS + threadIdx.x) * UPD_CELLS;
-		if (cell >= KN)
-			return;
+		size_t cell = ((size_t)blockIdx.x * UPD_THREADS + threadIdx.x) * UPD_CELLS;
+		const bool live_thread = cell < KN;
+		if (!live_thread)
+			cell = 0;
+		/* state + first group of counts are requested before the LUT is staged */
 		float2 hv = *reinterpret_cast<const float2 *>(a.hist + cell);
-		bool dirty = false;
 		const int total = a.n_calls * a.splits;
 		const unsigned *cnt = reinterpret_cast<const unsigned *>(a.cnt + cell);   /* 2 x u16 */
 		const size_t stride = KN / 2;                                              /* in 32-bit words */
+		unsigned w[UPD_SLICES];
+#pragma unroll
+		for (int u = 0; u < UPD_SLICES; u++)
+			w[u] = (u < total) ? __ldcg(cnt + (size_t)u * stride) : 0u;
+		for (int i = threadIdx.x; i <= a.batch; i += UPD_THREADS)
+			sh_lut[i] = __ldg(&a.lut[i]);
+		__syncthreads();
+		if (!live_thread)
+			return;
+		bool dirty = false;
 		unsigned hc0 = 0, hc1 = 0;
 		int in_call = 0;
 		for (int j0 = 0; j0 < total; j0 += UPD_SLICES) {
-			unsigned w[UPD_SLICES];
+			if (j0 > 0) {
 #pragma unroll
-			for (int u = 0; u < UPD_SLICES; u++)
-				w[u] = (j0 + u < total) ? __ldcg(cnt + (size_t)(j0 + u) * stride) : 0u;
+				for (int u = 0; u < UPD_SLICES; u++)
+					w[u] = (j0 + u < total) ? __ldcg(cnt + (size_t)(j0 + u) * stride) : 0u;
+			}
 #pragma unroll
 			for (int u = 0; u < UPD_SLICES; u++) {
 				if (j0 + u < total) {

@@ -214,8 +214,12 @@ bool plan_supported(int n)
 template <class P>
 cudaError_t stream_setup()
 {
-	return cudaFuncSetAttribute(fft_power_stream_kernel<P>,
+	cudaError_t err = cudaFuncSetAttribute(fft_power_stream_kernel<P, false>,
 		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamCfg<P>::SMEM);
+	if (err != cudaSuccess)
+		return err;
+	return cudaFuncSetAttribute(fft_power_stream_kernel<P, true>,
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamCfg<P>::SMEM_TWREG);
 }
 
 template <class P>
@@ -227,8 +231,12 @@ cudaError_t stream_launch(fosphor_cu *e, const float2 *in, long long hop, int wf
 	if (grid > resident)
 		grid = resident;                 /* persistent warps, grid-stride over spectra */
 	prof_mark(e, 0, 0);
-	fft_power_stream_kernel<P><<<grid, C::THREADS, C::SMEM, e->stream>>>(
-		in, hop, e->d_win, e->d_tw, e->d_wf, wf_pos, e->p.wf_rows - 1, n_spectra);
+	if (e->fft_variant == 2)
+		fft_power_stream_kernel<P, true><<<grid, C::THREADS, C::SMEM_TWREG, e->stream>>>(
+			in, hop, e->d_win, e->d_tw, e->d_wf, wf_pos, e->p.wf_rows - 1, n_spectra);
+	else
+		fft_power_stream_kernel<P, false><<<grid, C::THREADS, C::SMEM, e->stream>>>(
+			in, hop, e->d_win, e->d_tw, e->d_wf, wf_pos, e->p.wf_rows - 1, n_spectra);
 	prof_mark(e, 0, 1);
 	e->launches++;
 	return cudaGetLastError();

@@ -223,11 +223,17 @@ struct StreamCfg {
 	static constexpr int THREADS = WARPS * 32;
 	static constexpr int CTAS_PER_SM = 3;
 	static constexpr int BUF_ELEMS = P::SM_ELEMS;                 /* >= N: holds inputs, then the exchange */
-	static constexpr size_t SMEM = sizeof(float2) * (size_t)BUF_ELEMS * 2 * WARPS + 8 * 2 * WARPS;
+	static constexpr size_t BUF_BYTES_ALL = sizeof(float2) * (size_t)BUF_ELEMS * 2 * WARPS;
+	static constexpr size_t SMEM = BUF_BYTES_ALL + 8 * 2 * WARPS;
+	/* TWREG variant: + the window, shared by the CTA */
+	static constexpr size_t SMEM_TWREG = SMEM + sizeof(float) * P::N;
 	static constexpr unsigned IN_BYTES = sizeof(float2) * P::N;
 };
 
-template <class P>
+/* TWREG = false: window slice in registers, pass-1 twiddles fetched (L1) per spectrum.
+ * TWREG = true : pass-1 twiddles in registers for the lifetime of the warp, window
+ *                read from shared memory - no global load at all in the steady state. */
+template <class P, bool TWREG>
 __global__ void __launch_bounds__(StreamCfg<P>::THREADS, StreamCfg<P>::CTAS_PER_SM)
 fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
                         const float *__restrict__ win, const float2 *__restrict__ tw,
@@ -254,12 +260,26 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 	}
 	__syncwarp();
 
-	/* window slice of this lane: pass 0 element (lane + t*NB0) for the R0 registers */
-	float wreg[R0];
-	if (lane < P::NB0) {
+	/* window: registers (slice of this lane: pass-0 element lane + t*NB0) or shared memory */
+	float wreg[TWREG ? 1 : R0];
+	const float *swin = reinterpret_cast<const float *>(smem_raw + C::SMEM);
+	float2 twreg[TWREG ? R1 : 1];
+	if constexpr (TWREG) {
+		float *sw = reinterpret_cast<float *>(smem_raw + C::SMEM);
+		for (int i = threadIdx.x; i < N; i += C::THREADS)
+			sw[i] = __ldg(&win[i]);
+		__syncthreads();
+		if (lane < P::NB1) {
 #pragma unroll
-		for (int t = 0; t < R0; t++)
-			wreg[t] = __ldg(&win[lane + t * P::NB0]);
+			for (int t = 1; t < R1; t++)
+				twreg[t] = __ldg(&tw[t * R0 + (lane & (R0 - 1))]);
+		}
+	} else {
+		if (lane < P::NB0) {
+#pragma unroll
+			for (int t = 0; t < R0; t++)
+				wreg[t] = __ldg(&win[lane + t * P::NB0]);
+		}
 	}
 
 	int s = gw;
@@ -294,7 +314,8 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 #pragma unroll
 			for (int t = 0; t < R0; t++) {
 				const float2 x = buf[lane + t * P::NB0];
-				v0[t] = make_float2(x.x * wreg[t], x.y * wreg[t]);   /* fft.cl:416-417 */
+				const float w = TWREG ? swin[lane + t * P::NB0] : wreg[t];
+				v0[t] = make_float2(x.x * w, x.y * w);               /* fft.cl:416-417 */
 			}
 		}
 		__syncwarp();                   /* inputs consumed: buf becomes the exchange buffer */
@@ -316,7 +337,7 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 				v[t] = buf[pad_idx<P>(lane + t * P::NB1)];
 #pragma unroll
 			for (int t = 1; t < R1; t++)
-				v[t] = cmul(v[t], __ldg(&tw[t * R0 + k]));
+				v[t] = cmul(v[t], TWREG ? twreg[t] : __ldg(&tw[t * R0 + k]));
 			dif<R1>(v);
 			static_for<0, R1>([&](auto tc) {
 				constexpr int t = decltype(tc)::value;
