@@ -37,7 +37,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 N_FFT, N_BINS, OVERLAP, BATCH, CALLS_PER_STEP = 1024, 256, 4, 1024, 384
-WF_ROWS = 8192   # device ring: the FFT pass is launched once per 8 calls (8192 spectra)
+WF_ROWS = 32768  # device waterfall ring: the FFT pass is launched once per 16-32 calls
 REF_CALLS_PER_STEP = 8   # reference arm: one sink frame (base_sink_c_impl.cc:133-146) per step
 
 

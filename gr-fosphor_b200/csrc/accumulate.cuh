@@ -79,6 +79,23 @@ __device__ __forceinline__ int map_bin(float x, int kmax)
 	return min(max(__float2int_rz(r), 0), kmax);
 }
 
+/* Write the CTA's hit tile hits[K][32] (u32 in shared memory) to
+ * cnt[slice][K][N] as u16: a half-warp packs one bin row (16 x 2 columns) into
+ * 32-bit words, so each store instruction writes two bin rows of 64 bytes. */
+__device__ __forceinline__ void store_tile(const AccumArgs &a, const unsigned *sh_hits, int slice, int tile)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int K = a.n_bins, N = a.n;
+	const int sub = lane >> 4, pair = lane & 15;
+	unsigned *dst = reinterpret_cast<unsigned *>(a.cnt + (size_t)slice * K * N + tile * ACC_COLS) + pair;
+	const size_t row_words = (size_t)N / 2;
+#pragma unroll 4
+	for (int bin = 2 * warp + sub; bin < K; bin += 2 * ACC_WARPS) {
+		const uint2 h = *reinterpret_cast<const uint2 *>(sh_hits + bin * 32 + 2 * pair);
+		dst[(size_t)bin * row_words] = (h.x & 0xffffu) | (h.y << 16);
+	}
+}
+
 constexpr int ROWBLOCK = 128;     /* canonical unit of the f32 live partial sums */
 constexpr int BLK_GROUP = 8;      /* row blocks reduced per pass through shared memory */
 
@@ -187,10 +204,7 @@ count_kernel(const AccumArgs a)
 		__syncthreads();
 	}
 
-	unsigned short *dst = a.cnt + (size_t)slice * K * N + col;
-#pragma unroll 4
-	for (int bin = warp; bin < K; bin += ACC_WARPS)
-		dst[(size_t)bin * N] = (unsigned short)sh_hits[bin * 32 + lane];
+	store_tile(a, sh_hits, slice, tile);
 }
 
 /* ---- TMA-staged variant of count_kernel ----------------------------------- */
@@ -338,30 +352,27 @@ count_tma_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 			__syncthreads();
 	}
 
-	unsigned short *dst = a.cnt + (size_t)slice * K * N + col;
-#pragma unroll 4
-	for (int bin = warp; bin < K; bin += ACC_WARPS)
-		dst[(size_t)bin * N] = (unsigned short)sh_hits[bin * 32 + lane];
+	store_tile(a, sh_hits, slice, tile);
 }
 
-constexpr int UPD_CELLS = 2;      /* adjacent cells per thread (one 32-bit load of two u16 counts) */
+constexpr int UPD_CELLS = 4;      /* adjacent cells per thread (one 64-bit load of four u16 counts) */
 constexpr int UPD_SLICES = 8;     /* slices whose loads are issued together */
 constexpr int UPD_COLS = 32;      /* columns per live/max-hold block */
 
-__device__ __forceinline__ float rise_decay(float hv, unsigned hc, const float2 *lut, bool &dirty)
+/* display.cl:237-250 without a branch: cells with hv <= 0.01 and no hit keep
+ * their value exactly (the reference skips the write), everything else takes
+ * hv <- clamp((hv - d) e + d) with (d, e) from the per-batch table. */
+__device__ __forceinline__ float rise_decay(float hv, unsigned hc, const float2 *lut)
 {
-	if (hv <= 0.01f && hc == 0)                             /* display.cl:237-238 */
-		return hv;
 	const float2 de = lut[hc];
-	hv = __fadd_rn(__fmul_rn(__fsub_rn(hv, de.x), de.y), de.x);       /* :247 */
-	dirty = true;
-	return fminf(fmaxf(hv, 0.0f), 1.0f);                              /* :250 */
+	const float nv = fminf(fmaxf(__fadd_rn(__fmul_rn(__fsub_rn(hv, de.x), de.y), de.x), 0.0f), 1.0f);
+	return (hv <= 0.01f && hc == 0) ? hv : nv;
 }
 
 /* blocks [0, cell_blocks): one thread per UPD_CELLS adjacent histogram cells
- * (bin-major: a warp covers 64 consecutive columns of one bin); blocks beyond:
- * UPD_COLS columns each for live / max-hold.  N is even, so a cell pair never
- * straddles two bins. */
+ * (bin-major: a warp covers 128 consecutive columns of one bin); blocks beyond:
+ * UPD_COLS columns each for live / max-hold.  N is a multiple of 4, so a cell
+ * group never straddles two bins. */
 __global__ void __launch_bounds__(UPD_THREADS)
 update_kernel(const AccumArgs a, int cell_blocks)
 {
@@ -375,44 +386,57 @@ update_kernel(const AccumArgs a, int cell_blocks)
 		if (!live_thread)
 			cell = 0;
 		/* state + first group of counts are requested before the LUT is staged */
-		float2 hv = *reinterpret_cast<const float2 *>(a.hist + cell);
+		const float4 hv0 = *reinterpret_cast<const float4 *>(a.hist + cell);
 		const int total = a.n_calls * a.splits;
-		const unsigned *cnt = reinterpret_cast<const unsigned *>(a.cnt + cell);   /* 2 x u16 */
-		const size_t stride = KN / 2;                                              /* in 32-bit words */
-		unsigned w[UPD_SLICES];
+		const uint2 *cnt = reinterpret_cast<const uint2 *>(a.cnt + cell);          /* 4 x u16 */
+		const size_t stride = KN / 4;                                              /* in uint2 */
+		uint2 w[UPD_SLICES];
 #pragma unroll
 		for (int u = 0; u < UPD_SLICES; u++)
-			w[u] = (u < total) ? __ldcg(cnt + (size_t)u * stride) : 0u;
+			w[u] = (u < total) ? __ldcg(cnt + (size_t)u * stride) : make_uint2(0u, 0u);
 		for (int i = threadIdx.x; i <= a.batch; i += UPD_THREADS)
 			sh_lut[i] = __ldg(&a.lut[i]);
 		__syncthreads();
 		if (!live_thread)
 			return;
-		bool dirty = false;
-		unsigned hc0 = 0, hc1 = 0;
+		float4 hv = hv0;
+		unsigned hc0 = 0, hc1 = 0, hc2 = 0, hc3 = 0;
 		int in_call = 0;
+		const uint2 *p = cnt + (size_t)UPD_SLICES * stride;
 		for (int j0 = 0; j0 < total; j0 += UPD_SLICES) {
 			if (j0 > 0) {
 #pragma unroll
-				for (int u = 0; u < UPD_SLICES; u++)
-					w[u] = (j0 + u < total) ? __ldcg(cnt + (size_t)(j0 + u) * stride) : 0u;
+				for (int u = 0; u < UPD_SLICES; u++) {
+					w[u] = (j0 + u < total) ? __ldcg(p) : make_uint2(0u, 0u);
+					p += stride;
+				}
 			}
 #pragma unroll
 			for (int u = 0; u < UPD_SLICES; u++) {
-				if (j0 + u < total) {
-					hc0 += w[u] & 0xffffu;
-					hc1 += w[u] >> 16;
+				if (j0 + u < total) {                   /* warp-uniform */
+					hc0 += w[u].x & 0xffffu;
+					hc1 += w[u].x >> 16;
+					hc2 += w[u].y & 0xffffu;
+					hc3 += w[u].y >> 16;
 					if (++in_call == a.splits) {        /* all slices of this call summed */
-						hv.x = rise_decay(hv.x, hc0, sh_lut, dirty);
-						hv.y = rise_decay(hv.y, hc1, sh_lut, dirty);
-						hc0 = hc1 = 0;
+						/* nothing to do for a warp whose cells are all empty and unhit
+						 * (most of the plane): display.cl:237-238 */
+						const bool idle = (hc0 | hc1 | hc2 | hc3) == 0 &&
+						                  fmaxf(fmaxf(hv.x, hv.y), fmaxf(hv.z, hv.w)) <= 0.01f;
+						if (!__all_sync(0xffffffffu, idle)) {
+							hv.x = rise_decay(hv.x, hc0, sh_lut);
+							hv.y = rise_decay(hv.y, hc1, sh_lut);
+							hv.z = rise_decay(hv.z, hc2, sh_lut);
+							hv.w = rise_decay(hv.w, hc3, sh_lut);
+						}
+						hc0 = hc1 = hc2 = hc3 = 0;
 						in_call = 0;
 					}
 				}
 			}
 		}
-		if (dirty)
-			*reinterpret_cast<float2 *>(a.hist + cell) = hv;
+		if (hv.x != hv0.x || hv.y != hv0.y || hv.z != hv0.z || hv.w != hv0.w)
+			*reinterpret_cast<float4 *>(a.hist + cell) = hv;
 		return;
 	}
 

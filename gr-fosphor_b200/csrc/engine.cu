@@ -93,8 +93,9 @@ struct fosphor_cu {
 	BatchTables tables[N_TABLES];
 	unsigned long long use_clock = 0;
 	unsigned long long launches = 0;
-	int fft_variant = 1;                 /* 1: TMA-prefetching persistent kernel where applicable
-	                                      * 0: plain kernel (env FOSPHOR_B200_FFT_VARIANT=0)  */
+	int fft_variant = 2;                 /* env FOSPHOR_B200_FFT_VARIANT, N = 512/1024 with aligned input:
+	                                      * 2: TMA-prefetching persistent kernel, twiddles in registers
+	                                      * 1: same, twiddles fetched per spectrum   0: plain kernel */
 
 	/* optional per-kernel timing (bench.py roofline): event pairs around launches */
 	bool profiling = false;
@@ -305,17 +306,37 @@ int get_tables(fosphor_cu *e, int batch, BatchTables **out)
 /* How the calls of one launch are cut into slices (CTAs along the row axis).
  * Only hit counts (integers) and per-ROWBLOCK partial sums cross slice
  * boundaries, so the results are bit-identical for any slicing; the choice is
- * purely about filling the chip: at least ~2 CTAs per SM when there is work. */
+ * purely about keeping the SMs evenly busy: pick the split count whose CTA
+ * grid quantises best against the number of resident CTAs (every slice also
+ * pays a fixed cost for clearing and storing its hit tile). */
 void choose_slicing(const fosphor_cu *e, int n_calls, int batch, int *splits, int *rows_per_split)
 {
 	const int tiles = e->p.fft_len / ACC_COLS;
-	const int target = 2 * e->sm_count;
 	const int blocks = (batch + ROWBLOCK - 1) / ROWBLOCK;
-	int s = (target + tiles * n_calls - 1) / (tiles * n_calls);
-	if (s > blocks) s = blocks;
-	if (s > e->max_slices / n_calls) s = e->max_slices / n_calls;
-	if (s < 1) s = 1;
-	const int rows = (blocks + s - 1) / s * ROWBLOCK;
+	const size_t smem = sizeof(unsigned) * 32 * (size_t)e->p.n_bins + sizeof(CountStage) + 1024;
+	int per_sm = (int)((size_t)227 * 1024 / smem);
+	if (per_sm < 1) per_sm = 1;
+	if (per_sm > 8) per_sm = 8;
+	const long resident = (long)per_sm * e->sm_count;
+	const int overhead_rows = 24 + e->p.n_bins / 16;       /* tile clear + store, in row-equivalents */
+	int best_s = 1;
+	double best_cost = 1e300;
+	for (int s = 1; s <= blocks; s++) {
+		if ((long)s * n_calls > e->max_slices)
+			break;
+		const int rows = (blocks + s - 1) / s * ROWBLOCK;
+		const int real_s = (batch + rows - 1) / rows;
+		const long ctas = (long)tiles * n_calls * real_s;
+		const long waves = (ctas + resident - 1) / resident;
+		/* a partially filled last wave still runs at per-CTA speed */
+		const double cost = (double)waves * (rows + overhead_rows) *
+		                    (ctas < resident ? (double)((ctas + e->sm_count - 1) / e->sm_count) / per_sm : 1.0);
+		if (cost < best_cost - 1e-9) {
+			best_cost = cost;
+			best_s = real_s;
+		}
+	}
+	const int rows = (blocks + best_s - 1) / best_s * ROWBLOCK;
 	*rows_per_split = rows;
 	*splits = (batch + rows - 1) / rows;
 }
@@ -360,7 +381,7 @@ int launch_accumulate(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cuda
 	if (count_done)
 		CU_CHECK(e, cudaEventRecord(count_done, st));   /* the ring rows of this chunk are free again */
 	const size_t cells = (size_t)e->p.n_bins * e->p.fft_len;
-	const size_t per_block = (size_t)UPD_THREADS * UPD_CELLS;
+	const size_t per_block = (size_t)UPD_THREADS * UPD_CELLS;   /* N is a multiple of 512: no straddling */
 	const int cell_blocks = (int)((cells + per_block - 1) / per_block);
 	const int col_blocks = (e->p.fft_len + UPD_COLS - 1) / UPD_COLS;
 	size_t lut_smem = sizeof(float2) * (size_t)(batch + 1);
