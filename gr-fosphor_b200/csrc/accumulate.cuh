@@ -297,7 +297,7 @@ count_tma_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 	__syncthreads();
 
 	const int kmax = K - 1;
-	unsigned *my_hits = sh_hits + lane;
+	const unsigned hits_addr = cnt_smem_u32(sh_hits + lane);     /* + bin * 128 bytes */
 	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
 	const size_t part_base = (size_t)call * blocks_per_call + (size_t)(row0 / ROWBLOCK);
 	unsigned phases = 0u;                    /* bit d = parity to wait for on slot d */
@@ -319,18 +319,24 @@ count_tma_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 				} while (!ok);
 				phases ^= 1u << slot;
 				const float *rp = &st.rows[warp][slot][0][lane];
+				/* all 16 rows into registers first: the shared-memory increments below
+				 * may not be reordered against shared loads, and 16 independent
+				 * dependency chains are what keeps the issue slots busy */
+				float pw[WARP_ROWS];
 #pragma unroll
-				for (int r = 0; r < WARP_ROWS; r++) {
-					const float pw = rp[r * 32];
-					live = fmaf(pw, __shfl_sync(0xffffffffu, wts, r), live);      /* display.cl:149-150 */
-					mx = fmaxf(mx, pw);                                           /* :139 */
-					const int bin = map_bin(__fmul_rn(a.hscale, __fadd_rn(pw, a.hofs)), kmax);
-					atomicAdd(my_hits + bin * 32, 1u);                            /* :170-177 */
-				}
+				for (int r = 0; r < WARP_ROWS; r++)
+					pw[r] = rp[r * 32];
 				__syncwarp();                        /* the slot is consumed by every lane */
 				if (lane == 0 && blk + TMA_DEPTH < nblocks) {
 					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 					issue(blk + TMA_DEPTH);
+				}
+#pragma unroll
+				for (int r = 0; r < WARP_ROWS; r++) {
+					live = fmaf(pw[r], __shfl_sync(0xffffffffu, wts, r), live);   /* display.cl:149-150 */
+					mx = fmaxf(mx, pw[r]);                                        /* :139 */
+					const int bin = map_bin(__fmul_rn(a.hscale, __fadd_rn(pw[r], a.hofs)), kmax);
+					asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hits_addr + ((unsigned)bin << 7)) : "memory");   /* :170-177 */
 				}
 			}
 			st.live[blk - g0][warp][lane] = live;
@@ -356,7 +362,7 @@ count_tma_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 }
 
 constexpr int UPD_CELLS = 4;      /* adjacent cells per thread (one 64-bit load of four u16 counts) */
-constexpr int UPD_SLICES = 8;     /* slices whose loads are issued together */
+constexpr int UPD_SLICES = 16;    /* slices whose loads are issued together */
 constexpr int UPD_COLS = 32;      /* columns per live/max-hold block */
 
 /* display.cl:237-250 without a branch: cells with hv <= 0.01 and no hit keep
