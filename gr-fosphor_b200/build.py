@@ -6,14 +6,14 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfosphor_b200.so")
-SOURCES = ["engine.cu", "dropin.cu"]
-HEADERS = ["fft_regs.cuh", "fft_power.cuh", "accumulate.cuh"]
+SOURCES = ["engine.cu", "dropin.cu", "../host/pinned_fifo.cc"]
+HEADERS = ["fft_regs.cuh", "fft_power.cuh", "accumulate.cuh", "../host/pinned_fifo.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-fno-fast-math,-ffp-contract=off",
-    "-shared", "-cudart", "static",
+    "-shared", "-cudart", "static", "-x", "cu",
 ]
 
 

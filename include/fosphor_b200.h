@@ -155,6 +155,26 @@ int fosphor_cu_profile_read(struct fosphor_cu *e, double *ms, unsigned long long
 unsigned long long fosphor_cu_launch_count(const struct fosphor_cu *e);
 const char *fosphor_cu_last_error(const struct fosphor_cu *e);
 
+/* ------------------------------------------------------------------------ */
+/* 3. Page-locked sample FIFO (sink side)                    */
+/* ------------------------------------------------------------------------ */
+/* C handle of fosphor_b200::pinned_fifo (gr-fosphor_b200/host/pinned_fifo.h):
+ * the reference's gr::fosphor::fifo (lib/fifo.h:20-46) with page-locked
+ * storage, so process() DMAs straight out of the ring.  length: power of two,
+ * in complex samples.  write_prepare / read_peek return NULL when wait == 0
+ * and the request cannot be met. */
+void *fosphor_fifo_create(int length);
+void  fosphor_fifo_destroy(void *fifo);
+int   fosphor_fifo_is_pinned(void *fifo);
+int   fosphor_fifo_free(void *fifo);
+int   fosphor_fifo_used(void *fifo);
+int   fosphor_fifo_write_max_size(void *fifo);
+int   fosphor_fifo_read_max_size(void *fifo);
+void *fosphor_fifo_write_prepare(void *fifo, int size, int wait);
+void  fosphor_fifo_write_commit(void *fifo, int size);
+void *fosphor_fifo_read_peek(void *fifo, int size, int wait);
+void  fosphor_fifo_read_discard(void *fifo, int size);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,3 +67,39 @@ def test_dropin_release_is_null_safe_and_idempotent():
     eng.lib.fosphor_cl_release(C.byref(s))
     eng.lib.fosphor_cl_release(C.byref(s))
     assert not s.cl
+
+
+def test_pinned_fifo_feeds_the_dropin_without_staging():
+    """samples written into the page-locked FIFO are handed to
+    fosphor_cl_process() straight from the ring (DMA, no staging memcpy) and
+    discarded right after the call returns, like base_sink_c_impl::render()
+    (lib/base_sink_c_impl.cc:146-175); results match the oracle."""
+    import ctypes as C
+    import oracle_lib
+    import signals
+    from test_pinned_fifo import _lib
+    L = _lib()
+    f = L.fosphor_fifo_create(1 << 21)              # the sink's 2 Mi-sample ring (base_sink_c_impl.cc:58)
+    assert f and L.fosphor_fifo_is_pinned(f) == 1
+    eng = _dropin()
+    orc = oracle_lib.Oracle()
+    x = signals.noise_tones(1024 * (256 + 1024 + 64), seed=23)
+    pos = 0
+    for b in (256, 1024, 64):
+        n = b * 1024
+        dst = L.fosphor_fifo_write_prepare(f, n, 1)
+        C.memmove(dst, x[pos:pos + n].ctypes.data, 8 * n)
+        L.fosphor_fifo_write_commit(f, n)
+        src = L.fosphor_fifo_read_peek(f, n, 0)
+        assert src
+        assert eng.process_raw(src, n) == 0
+        L.fosphor_fifo_read_discard(f, n)           # legal at once: the call has consumed the buffer
+        C.memset(src, 0xff, 8 * n)                  # and the producer may overwrite it
+        assert orc.process(x[pos:pos + n]) == 0
+        pos += n
+    assert eng.finish() == 1 and orc.finish() == 1
+    parity.check_waterfall(eng.img_waterfall, orc.waterfall)
+    parity.check_histogram(eng.img_histogram, orc.histogram, hits_in_play=(256 + 1024 + 64) * 1024)
+    parity.check_spectrum(eng.buf_spectrum, orc.spectrum, wf_ref=orc.waterfall)
+    eng.release()
+    L.fosphor_fifo_destroy(f)
