@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfosphor_b200.so")
-SOURCES = ["engine.cu", "dropin.cu", "../host/pinned_fifo.cc"]
+SOURCES = ["engine.cu", "dropin.cu", "../host/pinned_fifo.cc", "../host/window.cc"]
 HEADERS = ["fft_regs.cuh", "fft_power.cuh", "accumulate.cuh", "../host/pinned_fifo.h"]
 
 NVCC_FLAGS = [

@@ -65,18 +65,21 @@ struct AccumArgs {
 	float mh_keep, mh_mix;    /* display.cl:303 */
 };
 
-__device__ __forceinline__ int map_bin(float x, int kmax)
+/* display.cl:161-165: bin = (int)round(histo_scale * (pwr + histo_ofs)), round
+ * half away from zero, clamped to [0, K-1].  Returned as the BYTE OFFSET of the
+ * bin row in the hits[K][32] u32 tile (bin * 128).
+ *   round_half_away(x) = (floor(2x) + 1) >> 1        for x >= 0 (exact, ties included)
+ * and 2x = (2*hscale) * (pwr + hofs) is the very same rounding as x (scaling by
+ * two is exact), so one float->int conversion replaces rint + tie fix-up.
+ * Negative x land on bin 0 through the lower clamp; the conversion saturates:
+ * NaN -> 0, -inf -> bin 0, +inf -> bin K-1, which is what the reference yields
+ * on the NVIDIA OpenCL runtime (golden case zeros_then_data) and is fixed as
+ * the rule in DESIGN.md. */
+__device__ __forceinline__ unsigned bin_row_offset(float pwr, float hofs, float hscale2, int kmax2)
 {
-	/* display.cl:161-165: (int)round(x), half away from zero, clamped to
-	 * [0, K-1].  rint() + a bump on exact .5 ties is round-half-away for x >= 0
-	 * (negative x clamp to 0 either way); the float->int conversion saturates,
-	 * so NaN -> 0, -inf -> 0, +inf -> K-1: what the reference yields on the
-	 * NVIDIA OpenCL runtime (golden case zeros_then_data), fixed as the rule in
-	 * DESIGN.md. */
-	float r = rintf(x);
-	if (x - r == 0.5f)
-		r += 1.0f;
-	return min(max(__float2int_rz(r), 0), kmax);
+	const int i = __float2int_rd(__fmul_rn(hscale2, __fadd_rn(pwr, hofs)));
+	const int j = min(max(i, -1), kmax2) + 1;        /* 0 .. 2*kmax + 1 */
+	return ((unsigned)j & ~1u) << 6;                 /* (j >> 1) * 128 */
 }
 
 /* Write the CTA's hit tile hits[K][32] (u32 in shared memory) to
@@ -106,8 +109,8 @@ struct RowCtx {
 	const float *weights;
 	unsigned *my_hits;        /* sh_hits + lane */
 	unsigned ring0, mask, n;
-	float hscale, hofs;
-	int kmax;
+	float hscale2, hofs;      /* 2 * histo_scale, histo_ofs */
+	int kmax2;                /* 2 * (K - 1) */
 };
 
 /* U consecutive rows s .. s+U-1 of one column per lane: all loads first, then
@@ -126,8 +129,8 @@ __device__ __forceinline__ void count_rows(const RowCtx &c, int s, float &live, 
 	for (int u = 0; u < U; u++) {
 		live = fmaf(pw[u], wt[u], live);                                  /* display.cl:149-150 */
 		mx = fmaxf(mx, pw[u]);                                            /* :139 */
-		const int bin = map_bin(__fmul_rn(c.hscale, __fadd_rn(pw[u], c.hofs)), c.kmax);
-		atomicAdd(c.my_hits + bin * 32, 1u);                              /* :170-177 */
+		const unsigned off = bin_row_offset(pw[u], c.hofs, c.hscale2, c.kmax2);   /* :161-165 */
+		atomicAdd(c.my_hits + (off >> 2), 1u);                            /* :170-177 */
 	}
 }
 
@@ -166,9 +169,9 @@ count_kernel(const AccumArgs a)
 	c.ring0 = (unsigned)(a.wf_pos + call * a.batch);
 	c.mask = (unsigned)a.wf_mask;
 	c.n = (unsigned)N;
-	c.hscale = a.hscale;
+	c.hscale2 = 2.0f * a.hscale;
 	c.hofs = a.hofs;
-	c.kmax = K - 1;
+	c.kmax2 = 2 * (K - 1);
 	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
 	const size_t part_base = (size_t)call * blocks_per_call;
 
@@ -296,7 +299,8 @@ count_tma_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 	}
 	__syncthreads();
 
-	const int kmax = K - 1;
+	const int kmax2 = 2 * (K - 1);
+	const float hscale2 = 2.0f * a.hscale;
 	const unsigned hits_addr = cnt_smem_u32(sh_hits + lane);     /* + bin * 128 bytes */
 	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
 	const size_t part_base = (size_t)call * blocks_per_call + (size_t)(row0 / ROWBLOCK);
@@ -335,8 +339,8 @@ count_tma_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 				for (int r = 0; r < WARP_ROWS; r++) {
 					live = fmaf(pw[r], __shfl_sync(0xffffffffu, wts, r), live);   /* display.cl:149-150 */
 					mx = fmaxf(mx, pw[r]);                                        /* :139 */
-					const int bin = map_bin(__fmul_rn(a.hscale, __fadd_rn(pw[r], a.hofs)), kmax);
-					asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hits_addr + ((unsigned)bin << 7)) : "memory");   /* :170-177 */
+					const unsigned off = bin_row_offset(pw[r], a.hofs, hscale2, kmax2);                /* :161-165 */
+					asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hits_addr + off) : "memory");     /* :170-177 */
 				}
 			}
 			st.live[blk - g0][warp][lane] = live;
@@ -364,6 +368,7 @@ count_tma_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 constexpr int UPD_CELLS = 4;      /* adjacent cells per thread (one 64-bit load of four u16 counts) */
 constexpr int UPD_SLICES = 16;    /* slices whose loads are issued together */
 constexpr int UPD_COLS = 32;      /* columns per live/max-hold block */
+constexpr int UPD_PARTS = 64;     /* live/max partials (call x row block) staged per pass */
 
 /* display.cl:237-250 without a branch: cells with hv <= 0.01 and no hit keep
  * their value exactly (the reference skips the write), everything else takes
@@ -446,48 +451,60 @@ update_kernel(const AccumArgs a, int cell_blocks)
 		return;
 	}
 
-	/* ---- live / max-hold: a block owns UPD_COLS columns.  All partials of the
-	 * chunk are fetched in parallel into shared memory first (the loads are
-	 * independent); then one thread per column runs the serial recurrences. ---- */
-	float *sh_part = reinterpret_cast<float *>(sh_lut);       /* [2][nparts][UPD_COLS] */
+	/* ---- live / max-hold: a block owns UPD_COLS columns.  The partials are
+	 * fetched UPD_PARTS at a time, in parallel, into shared memory (the loads are
+	 * independent); then one thread per column runs the serial recurrences over
+	 * the calls of that group. ---- */
+	float *sh_part = reinterpret_cast<float *>(sh_lut);       /* [2][cap][UPD_COLS] */
 	const int col0 = ((int)blockIdx.x - cell_blocks) * UPD_COLS;
 	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
-	const int nparts = a.n_calls * blocks_per_call;
-	for (int i = threadIdx.x; i < nparts * UPD_COLS; i += UPD_THREADS) {
-		const int p = i / UPD_COLS, c = i % UPD_COLS;
-		if (col0 + c < N) {
-			sh_part[i] = __ldcg(&a.part_live[(size_t)p * N + col0 + c]);
-			sh_part[nparts * UPD_COLS + i] = __ldcg(&a.part_max[(size_t)p * N + col0 + c]);
-		}
-	}
-	__syncthreads();
+	const int cap = max(UPD_PARTS, blocks_per_call);      /* staged partials per pass (host sizes smem alike) */
+	const int calls_per_group = cap / blocks_per_call;
 	const int col = col0 + threadIdx.x;
-	if (threadIdx.x >= UPD_COLS || col >= N)
-		return;
+	const bool owner = threadIdx.x < UPD_COLS && col < N;
 	const int half = N >> 1;
-	const int i = col ^ half;                                 /* display.cl:201 */
+	const int i = (owner ? col : 0) ^ half;                   /* display.cl:201 */
 	const float xpos = ((float)i / (float)half) - 1.0f;       /* :209 */
-	float y = a.spectrum[i].y;
-	float m = a.spectrum[N + i].y;
-	const float *pl = sh_part + threadIdx.x;
-	const float *pm = sh_part + nparts * UPD_COLS + threadIdx.x;
-	for (int c = 0; c < a.n_calls; c++) {
-		float sum = 0.0f, bmax = -1000.0f;
-		for (int b = 0; b < blocks_per_call; b++) {
-			sum += pl[(c * blocks_per_call + b) * UPD_COLS];
-			bmax = fmaxf(bmax, pm[(c * blocks_per_call + b) * UPD_COLS]);
-		}
-		/* live spectrum, display.cl:203-214 */
-		if (!isfinite(y))
-			y = sum / (float)REF_ROWS;
-		y = __fadd_rn(__fmul_rn(y, a.live_carry), __fmul_rn(sum, a.alpha));
-		/* max hold with decay, display.cl:287-309 */
-		if (!isfinite(m))
-			m = -FLT_MAX;
-		m = __fadd_rn(__fmul_rn(m, a.mh_keep), __fmul_rn(a.mh_mix, y));
-		m = fmaxf(m, bmax);
+	float y = 0.0f, m = 0.0f;
+	if (owner) {
+		y = a.spectrum[i].y;
+		m = a.spectrum[N + i].y;
 	}
-	if (a.n_calls > 0) {
+	for (int c0 = 0; c0 < a.n_calls; c0 += calls_per_group) {
+		const int nc = min(calls_per_group, a.n_calls - c0);
+		const int nparts = nc * blocks_per_call;
+		const size_t pbase = (size_t)c0 * blocks_per_call;
+		__syncthreads();                              /* previous group consumed */
+		for (int t = threadIdx.x; t < nparts * UPD_COLS; t += UPD_THREADS) {
+			const int p = t / UPD_COLS, c = t % UPD_COLS;
+			if (col0 + c < N) {
+				sh_part[t] = __ldcg(&a.part_live[(pbase + p) * N + col0 + c]);
+				sh_part[cap * UPD_COLS + t] = __ldcg(&a.part_max[(pbase + p) * N + col0 + c]);
+			}
+		}
+		__syncthreads();
+		if (owner) {
+			const float *pl = sh_part + threadIdx.x;
+			const float *pm = sh_part + cap * UPD_COLS + threadIdx.x;
+			for (int c = 0; c < nc; c++) {
+				float sum = 0.0f, bmax = -1000.0f;
+				for (int b = 0; b < blocks_per_call; b++) {
+					sum += pl[(c * blocks_per_call + b) * UPD_COLS];
+					bmax = fmaxf(bmax, pm[(c * blocks_per_call + b) * UPD_COLS]);
+				}
+				/* live spectrum, display.cl:203-214 */
+				if (!isfinite(y))
+					y = sum / (float)REF_ROWS;
+				y = __fadd_rn(__fmul_rn(y, a.live_carry), __fmul_rn(sum, a.alpha));
+				/* max hold with decay, display.cl:287-309 */
+				if (!isfinite(m))
+					m = -FLT_MAX;
+				m = __fadd_rn(__fmul_rn(m, a.mh_keep), __fmul_rn(a.mh_mix, y));
+				m = fmaxf(m, bmax);
+			}
+		}
+	}
+	if (owner && a.n_calls > 0) {
 		a.spectrum[i] = make_float2(xpos, y);
 		a.spectrum[N + i] = make_float2(xpos, m);
 	}

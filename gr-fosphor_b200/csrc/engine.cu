@@ -59,7 +59,10 @@ struct fosphor_cu {
 	cudaEvent_t fft_done[2] = {nullptr, nullptr};   /* ping-pong per chunk */
 	cudaEvent_t cnt_done[2] = {nullptr, nullptr};
 	cudaEvent_t acc_done = nullptr;
-	int overlap = 1;                     /* env FOSPHOR_B200_OVERLAP=0 puts everything on one stream */
+	int overlap = 0;                     /* env FOSPHOR_B200_OVERLAP=1: count/update of chunk c on a second
+	                                      * stream while the FFT of chunk c+1 runs.  Off by default: the FFT
+	                                      * kernel fills every SM's registers and shared memory, so nothing
+	                                      * co-resides with it and halving the chunks only costs (measured). */
 	CUtensorMap wf_tmap;                 /* waterfall ring as a 2-D tensor, box = 16 rows x 32 columns */
 	bool tmap_ok = false;
 	int count_variant = 1;               /* 1: TMA-staged count kernel where applicable, 0: plain
@@ -386,7 +389,9 @@ int launch_accumulate(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cuda
 	const int col_blocks = (e->p.fft_len + UPD_COLS - 1) / UPD_COLS;
 	size_t lut_smem = sizeof(float2) * (size_t)(batch + 1);
 	{
-		const size_t parts = (size_t)n_calls * ((batch + ROWBLOCK - 1) / ROWBLOCK);
+		size_t parts = (size_t)(batch + ROWBLOCK - 1) / ROWBLOCK;    /* at least one call per pass */
+		if (parts < UPD_PARTS)
+			parts = UPD_PARTS;
 		const size_t part_smem = sizeof(float) * 2 * parts * UPD_COLS;
 		if (part_smem > lut_smem)
 			lut_smem = part_smem;
@@ -447,13 +452,6 @@ int process_device_calls(fosphor_cu *e, const float2 *in, int n_calls, int batch
 			calls_per_chunk = ring_calls / 2;
 		if (calls_per_chunk > e->max_slices)
 			calls_per_chunk = e->max_slices;
-		{
-			/* the live/max partials of a chunk are staged in shared memory by update_kernel */
-			const int max_parts = (int)(UPD_SMEM_MAX / (sizeof(float) * 2 * UPD_COLS));
-			const int by_parts = max_parts / ((batch + ROWBLOCK - 1) / ROWBLOCK);
-			if (calls_per_chunk > by_parts)
-				calls_per_chunk = by_parts > 0 ? by_parts : 1;
-		}
 		cudaStream_t acc = two_streams ? e->acc_stream : e->stream;
 		int chunk = 0;
 		for (int c0 = 0; c0 < n_calls; c0 += calls_per_chunk, chunk++) {

@@ -175,6 +175,15 @@ void  fosphor_fifo_write_commit(void *fifo, int size);
 void *fosphor_fifo_read_peek(void *fifo, int size, int wait);
 void  fosphor_fifo_read_discard(void *fifo, int size);
 
+/* ------------------------------------------------------------------------ */
+/* 4. FFT window generator                                  */
+/* ------------------------------------------------------------------------ */
+/* What the sink obtains from gr::fft::window::build(type, 1024, 6.76)
+ * (lib/base_sink_c_impl.cc:251-255); type uses gr::fft::window::win_type
+ * numbering: 0 Hamming, 1 Hann, 2 Blackman, 3 rectangular, 4 Kaiser(beta),
+ * 5 Blackman-harris, 6 Bartlett, 7 flat-top.  0 / -1. */
+int fosphor_window_build(int type, int n, double beta, float *out);
+
 #ifdef __cplusplus
 }
 #endif
