@@ -20,7 +20,8 @@
  *      per column.  Nothing is read-modify-written in global memory, so there
  *      is nothing to clear between calls.
  *
- *  update_kernel (parallel over the K x N state cells and the N columns)
+ *  update_kernel + update_columns_kernel (parallel over the K x N state cells /
+ *  the N columns)
  *      The only sequential dependence of the whole path is along the CALL axis
  *      inside one cell:  hv <- (hv - d) e + d  with (d, e) a function of that
  *      call's hit count.  One thread owns one cell (or one column for
@@ -331,10 +332,10 @@ count_tma_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 				for (int r = 0; r < WARP_ROWS; r++)
 					pw[r] = rp[r * 32];
 				__syncwarp();                        /* the slot is consumed by every lane */
-				if (lane == 0 && blk + TMA_DEPTH < nblocks) {
-					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				/* the slot was only READ through the generic proxy; program order after
+				 * the warp barrier is all the async-proxy overwrite needs */
+				if (lane == 0 && blk + TMA_DEPTH < nblocks)
 					issue(blk + TMA_DEPTH);
-				}
 #pragma unroll
 				for (int r = 0; r < WARP_ROWS; r++) {
 					live = fmaf(pw[r], __shfl_sync(0xffffffffu, wts, r), live);   /* display.cl:149-150 */
@@ -380,18 +381,18 @@ __device__ __forceinline__ float rise_decay(float hv, unsigned hc, const float2 
 	return (hv <= 0.01f && hc == 0) ? hv : nv;
 }
 
-/* blocks [0, cell_blocks): one thread per UPD_CELLS adjacent histogram cells
- * (bin-major: a warp covers 128 consecutive columns of one bin); blocks beyond:
- * UPD_COLS columns each for live / max-hold.  N is a multiple of 4, so a cell
- * group never straddles two bins. */
+/* update_kernel: one thread per UPD_CELLS adjacent histogram cells (bin-major:
+ * a warp covers 128 consecutive columns of one bin; N is a multiple of 4, so a
+ * cell group never straddles two bins). */
 __global__ void __launch_bounds__(UPD_THREADS)
-update_kernel(const AccumArgs a, int cell_blocks)
+update_kernel(const AccumArgs a)
 {
 	extern __shared__ float2 sh_lut[];              /* [B+1] (d, e) */
 	const int K = a.n_bins, N = a.n;
 	const size_t KN = (size_t)K * N;
+	(void)N;
 
-	if ((int)blockIdx.x < cell_blocks) {
+	{
 		size_t cell = ((size_t)blockIdx.x * UPD_THREADS + threadIdx.x) * UPD_CELLS;
 		const bool live_thread = cell < KN;
 		if (!live_thread)
@@ -448,18 +449,22 @@ update_kernel(const AccumArgs a, int cell_blocks)
 		}
 		if (hv.x != hv0.x || hv.y != hv0.y || hv.z != hv0.z || hv.w != hv0.w)
 			*reinterpret_cast<float4 *>(a.hist + cell) = hv;
-		return;
 	}
+}
 
-	/* ---- live / max-hold: a block owns UPD_COLS columns.  The partials are
-	 * fetched UPD_PARTS at a time, in parallel, into shared memory (the loads are
-	 * independent); then one thread per column runs the serial recurrences over
-	 * the calls of that group. ---- */
-	float *sh_part = reinterpret_cast<float *>(sh_lut);       /* [2][cap][UPD_COLS] */
-	const int col0 = ((int)blockIdx.x - cell_blocks) * UPD_COLS;
+/* update_columns_kernel: live IIR and max-hold.  A block owns UPD_COLS columns;
+ * the partials of the chunk are fetched in parallel into shared memory (the
+ * loads are independent, `cap` partials per pass), then one thread per column
+ * runs the serial recurrences over the calls.  Independent of update_kernel,
+ * so the engine runs the two concurrently on two streams. */
+__global__ void __launch_bounds__(UPD_THREADS)
+update_columns_kernel(const AccumArgs a, int cap)
+{
+	extern __shared__ float sh_part[];                        /* [2][cap][UPD_COLS] */
+	const int N = a.n;
+	const int col0 = (int)blockIdx.x * UPD_COLS;
 	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
-	const int cap = max(UPD_PARTS, blocks_per_call);      /* staged partials per pass (host sizes smem alike) */
-	const int calls_per_group = cap / blocks_per_call;
+	const int calls_per_group = cap / blocks_per_call;    /* >= 1: cap >= blocks_per_call (host) */
 	const int col = col0 + threadIdx.x;
 	const bool owner = threadIdx.x < UPD_COLS && col < N;
 	const int half = N >> 1;

@@ -59,6 +59,7 @@ struct fosphor_cu {
 	cudaEvent_t fft_done[2] = {nullptr, nullptr};   /* ping-pong per chunk */
 	cudaEvent_t cnt_done[2] = {nullptr, nullptr};
 	cudaEvent_t acc_done = nullptr;
+	cudaEvent_t cols_fork = nullptr, cols_join = nullptr;   /* column update runs beside the cell update */
 	int overlap = 0;                     /* env FOSPHOR_B200_OVERLAP=1: count/update of chunk c on a second
 	                                      * stream while the FFT of chunk c+1 runs.  Off by default: the FFT
 	                                      * kernel fills every SM's registers and shared memory, so nothing
@@ -387,19 +388,31 @@ int launch_accumulate(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cuda
 	const size_t per_block = (size_t)UPD_THREADS * UPD_CELLS;   /* N is a multiple of 512: no straddling */
 	const int cell_blocks = (int)((cells + per_block - 1) / per_block);
 	const int col_blocks = (e->p.fft_len + UPD_COLS - 1) / UPD_COLS;
-	size_t lut_smem = sizeof(float2) * (size_t)(batch + 1);
-	{
-		size_t parts = (size_t)(batch + ROWBLOCK - 1) / ROWBLOCK;    /* at least one call per pass */
-		if (parts < UPD_PARTS)
-			parts = UPD_PARTS;
-		const size_t part_smem = sizeof(float) * 2 * parts * UPD_COLS;
-		if (part_smem > lut_smem)
-			lut_smem = part_smem;
+	const size_t lut_smem = sizeof(float2) * (size_t)(batch + 1);
+	/* partials staged per pass by the column kernel: the whole chunk if it fits */
+	const int blocks_per_call = (batch + ROWBLOCK - 1) / ROWBLOCK;
+	int cap = n_calls * blocks_per_call;
+	const int cap_max = (int)(UPD_SMEM_MAX / (sizeof(float) * 2 * UPD_COLS));
+	if (cap > cap_max)
+		cap = cap_max / blocks_per_call > 0 ? cap_max / blocks_per_call * blocks_per_call : blocks_per_call;
+	const size_t part_smem = sizeof(float) * 2 * (size_t)cap * UPD_COLS;
+
+	/* the cell update and the column (live / max-hold) update are independent:
+	 * run them side by side, the column kernel on the engine's second stream */
+	cudaStream_t cst = (e->acc_stream && e->acc_stream != st) ? e->acc_stream : st;
+	if (cst != st) {
+		CU_CHECK(e, cudaEventRecord(e->cols_fork, st));
+		CU_CHECK(e, cudaStreamWaitEvent(cst, e->cols_fork, 0));
 	}
+	update_columns_kernel<<<col_blocks, UPD_THREADS, part_smem, cst>>>(a, cap);
+	if (cst != st)
+		CU_CHECK(e, cudaEventRecord(e->cols_join, cst));
 	prof_mark(e, 2, 0, st);
-	update_kernel<<<cell_blocks + col_blocks, UPD_THREADS, lut_smem, st>>>(a, cell_blocks);
+	update_kernel<<<cell_blocks, UPD_THREADS, lut_smem, st>>>(a);
 	prof_mark(e, 2, 1, st);
-	e->launches += 2;
+	if (cst != st)
+		CU_CHECK(e, cudaStreamWaitEvent(st, e->cols_join, 0));
+	e->launches += 3;
 	CU_CHECK(e, cudaGetLastError());
 	return 0;
 }
@@ -579,6 +592,8 @@ void fosphor_cu_destroy(struct fosphor_cu *e)
 		if (e->cnt_done[i]) cudaEventDestroy(e->cnt_done[i]);
 	}
 	if (e->acc_done) cudaEventDestroy(e->acc_done);
+	if (e->cols_fork) cudaEventDestroy(e->cols_fork);
+	if (e->cols_join) cudaEventDestroy(e->cols_join);
 	if (e->own_stream) cudaStreamDestroy(e->own_stream);
 	delete e;
 }
@@ -638,6 +653,8 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 		CREATE_CHECK(cudaEventCreateWithFlags(&e->cnt_done[i], cudaEventDisableTiming));
 	}
 	CREATE_CHECK(cudaEventCreateWithFlags(&e->acc_done, cudaEventDisableTiming));
+	CREATE_CHECK(cudaEventCreateWithFlags(&e->cols_fork, cudaEventDisableTiming));
+	CREATE_CHECK(cudaEventCreateWithFlags(&e->cols_join, cudaEventDisableTiming));
 	if (const char *v = getenv("FOSPHOR_B200_OVERLAP"))
 		e->overlap = atoi(v);
 
@@ -689,11 +706,13 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 		if (const char *v = getenv("FOSPHOR_B200_FFT_VARIANT"))
 			e->fft_variant = atoi(v);
 	}
+	CREATE_CHECK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                                  (int)(sizeof(float2) * (size_t)(p.batch_max + 1))));
 	{
-		size_t upd = sizeof(float2) * (size_t)(p.batch_max + 1);
+		size_t upd = sizeof(float) * 2 * UPD_COLS * (size_t)((p.batch_max + ROWBLOCK - 1) / ROWBLOCK);
 		if (upd < UPD_SMEM_MAX)
 			upd = UPD_SMEM_MAX;
-		CREATE_CHECK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd));
+		CREATE_CHECK(cudaFuncSetAttribute(update_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd));
 	}
 	CREATE_CHECK(cudaFuncSetAttribute(count_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                                  (int)(sizeof(unsigned) * 32 * k + sizeof(CountStage))));
