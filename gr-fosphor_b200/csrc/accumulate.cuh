@@ -44,7 +44,7 @@ namespace fosphor_b200 {
 constexpr int ACC_COLS = 32;     /* columns per tile == warp width */
 constexpr int ACC_WARPS = 8;
 constexpr int ACC_THREADS = ACC_WARPS * 32;
-constexpr int UPD_THREADS = 256;
+constexpr int UPD_THREADS = 128;
 constexpr int REF_ROWS = 16;     /* display.cl:206-207 "sum / get_local_size(1)" */
 
 struct AccumArgs {
@@ -384,16 +384,14 @@ __device__ __forceinline__ float rise_decay(float hv, unsigned hc, const float2 
 /* update_kernel: one thread per UPD_CELLS adjacent histogram cells (bin-major:
  * a warp covers 128 consecutive columns of one bin; N is a multiple of 4, so a
  * cell group never straddles two bins). */
-__global__ void __launch_bounds__(UPD_THREADS)
-update_kernel(const AccumArgs a)
+__device__ __forceinline__ void update_cells(const AccumArgs &a, int block, float2 *sh_lut)
 {
-	extern __shared__ float2 sh_lut[];              /* [B+1] (d, e) */
 	const int K = a.n_bins, N = a.n;
 	const size_t KN = (size_t)K * N;
 	(void)N;
 
 	{
-		size_t cell = ((size_t)blockIdx.x * UPD_THREADS + threadIdx.x) * UPD_CELLS;
+		size_t cell = ((size_t)block * UPD_THREADS + threadIdx.x) * UPD_CELLS;
 		const bool live_thread = cell < KN;
 		if (!live_thread)
 			cell = 0;
@@ -452,17 +450,14 @@ update_kernel(const AccumArgs a)
 	}
 }
 
-/* update_columns_kernel: live IIR and max-hold.  A block owns UPD_COLS columns;
- * the partials of the chunk are fetched in parallel into shared memory (the
- * loads are independent, `cap` partials per pass), then one thread per column
- * runs the serial recurrences over the calls.  Independent of update_kernel,
- * so the engine runs the two concurrently on two streams. */
-__global__ void __launch_bounds__(UPD_THREADS)
-update_columns_kernel(const AccumArgs a, int cap)
+/* live IIR and max-hold.  A block owns UPD_COLS columns; the partials of the
+ * chunk are fetched in parallel into shared memory (independent loads, `cap`
+ * partials per pass), then one thread per column runs the serial recurrences
+ * over the calls of the pass. */
+__device__ __forceinline__ void update_columns(const AccumArgs &a, int block, int cap, float *sh_part)
 {
-	extern __shared__ float sh_part[];                        /* [2][cap][UPD_COLS] */
 	const int N = a.n;
-	const int col0 = (int)blockIdx.x * UPD_COLS;
+	const int col0 = block * UPD_COLS;
 	const int blocks_per_call = (a.batch + ROWBLOCK - 1) / ROWBLOCK;
 	const int calls_per_group = cap / blocks_per_call;    /* >= 1: cap >= blocks_per_call (host) */
 	const int col = col0 + threadIdx.x;
@@ -480,11 +475,30 @@ update_columns_kernel(const AccumArgs a, int cap)
 		const int nparts = nc * blocks_per_call;
 		const size_t pbase = (size_t)c0 * blocks_per_call;
 		__syncthreads();                              /* previous group consumed */
-		for (int t = threadIdx.x; t < nparts * UPD_COLS; t += UPD_THREADS) {
-			const int p = t / UPD_COLS, c = t % UPD_COLS;
-			if (col0 + c < N) {
-				sh_part[t] = __ldcg(&a.part_live[(pbase + p) * N + col0 + c]);
-				sh_part[cap * UPD_COLS + t] = __ldcg(&a.part_max[(pbase + p) * N + col0 + c]);
+		{
+			/* thread (p0, c): partials p0, p0 + 8, ... of column c; 8 loads in flight */
+			const int c = threadIdx.x % UPD_COLS, p0 = threadIdx.x / UPD_COLS;
+			constexpr int PSTEP = UPD_THREADS / UPD_COLS;
+			const bool okc = col0 + c < N;
+			const float *gl = a.part_live + pbase * N + col0 + c;
+			const float *gm = a.part_max + pbase * N + col0 + c;
+			for (int q0 = p0; q0 < nparts; q0 += 4 * PSTEP) {
+				float vl[4], vm[4];
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const int q = q0 + u * PSTEP;
+					const bool ok = okc && q < nparts;
+					vl[u] = ok ? __ldcg(gl + (size_t)q * N) : 0.0f;
+					vm[u] = ok ? __ldcg(gm + (size_t)q * N) : -1000.0f;
+				}
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const int q = q0 + u * PSTEP;
+					if (q < nparts) {
+						sh_part[q * UPD_COLS + c] = vl[u];
+						sh_part[(cap + q) * UPD_COLS + c] = vm[u];
+					}
+				}
 			}
 		}
 		__syncthreads();
@@ -513,6 +527,18 @@ update_columns_kernel(const AccumArgs a, int cap)
 		a.spectrum[i] = make_float2(xpos, y);
 		a.spectrum[N + i] = make_float2(xpos, m);
 	}
+}
+
+/* blocks [0, cell_blocks): histogram cells; blocks beyond: UPD_COLS columns each
+ * of live / max-hold.  The two roles are independent and share the launch. */
+__global__ void __launch_bounds__(UPD_THREADS)
+update_kernel(const AccumArgs a, int cell_blocks, int cap)
+{
+	extern __shared__ __align__(16) unsigned char upd_smem[];
+	if ((int)blockIdx.x < cell_blocks)
+		update_cells(a, (int)blockIdx.x, reinterpret_cast<float2 *>(upd_smem));
+	else
+		update_columns(a, (int)blockIdx.x - cell_blocks, cap, reinterpret_cast<float *>(upd_smem));
 }
 
 /* first-use state, cl.c:406-465 */

@@ -64,6 +64,8 @@ struct fosphor_cu {
 	                                      * stream while the FFT of chunk c+1 runs.  Off by default: the FFT
 	                                      * kernel fills every SM's registers and shared memory, so nothing
 	                                      * co-resides with it and halving the chunks only costs (measured). */
+	int fft_ctas_per_sm = 0;             /* env FOSPHOR_B200_FFT_CTAS: leave room beside the persistent FFT
+	                                      * kernel (e.g. 2) so count CTAs can co-reside in overlap mode */
 	CUtensorMap wf_tmap;                 /* waterfall ring as a 2-D tensor, box = 16 rows x 32 columns */
 	bool tmap_ok = false;
 	int count_variant = 1;               /* 1: TMA-staged count kernel where applicable, 0: plain
@@ -232,7 +234,8 @@ cudaError_t stream_launch(fosphor_cu *e, const float2 *in, long long hop, int wf
 {
 	using C = StreamCfg<P>;
 	int grid = (n_spectra + C::WARPS - 1) / C::WARPS;
-	const int resident = e->sm_count * C::CTAS_PER_SM;
+	const int resident = e->sm_count * (e->fft_ctas_per_sm > 0 && e->fft_ctas_per_sm < C::CTAS_PER_SM
+	                                        ? e->fft_ctas_per_sm : C::CTAS_PER_SM);
 	if (grid > resident)
 		grid = resident;                 /* persistent warps, grid-stride over spectra */
 	prof_mark(e, 0, 0);
@@ -389,30 +392,15 @@ int launch_accumulate(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cuda
 	const int cell_blocks = (int)((cells + per_block - 1) / per_block);
 	const int col_blocks = (e->p.fft_len + UPD_COLS - 1) / UPD_COLS;
 	const size_t lut_smem = sizeof(float2) * (size_t)(batch + 1);
-	/* partials staged per pass by the column kernel: the whole chunk if it fits */
+	/* partials staged per pass by the column blocks */
 	const int blocks_per_call = (batch + ROWBLOCK - 1) / ROWBLOCK;
-	int cap = n_calls * blocks_per_call;
-	const int cap_max = (int)(UPD_SMEM_MAX / (sizeof(float) * 2 * UPD_COLS));
-	if (cap > cap_max)
-		cap = cap_max / blocks_per_call > 0 ? cap_max / blocks_per_call * blocks_per_call : blocks_per_call;
+	const int cap = blocks_per_call > UPD_PARTS ? blocks_per_call : UPD_PARTS / blocks_per_call * blocks_per_call;
 	const size_t part_smem = sizeof(float) * 2 * (size_t)cap * UPD_COLS;
-
-	/* the cell update and the column (live / max-hold) update are independent:
-	 * run them side by side, the column kernel on the engine's second stream */
-	cudaStream_t cst = (e->acc_stream && e->acc_stream != st) ? e->acc_stream : st;
-	if (cst != st) {
-		CU_CHECK(e, cudaEventRecord(e->cols_fork, st));
-		CU_CHECK(e, cudaStreamWaitEvent(cst, e->cols_fork, 0));
-	}
-	update_columns_kernel<<<col_blocks, UPD_THREADS, part_smem, cst>>>(a, cap);
-	if (cst != st)
-		CU_CHECK(e, cudaEventRecord(e->cols_join, cst));
+	const size_t upd_smem = part_smem > lut_smem ? part_smem : lut_smem;
 	prof_mark(e, 2, 0, st);
-	update_kernel<<<cell_blocks, UPD_THREADS, lut_smem, st>>>(a);
+	update_kernel<<<cell_blocks + col_blocks, UPD_THREADS, upd_smem, st>>>(a, cell_blocks, cap);
 	prof_mark(e, 2, 1, st);
-	if (cst != st)
-		CU_CHECK(e, cudaStreamWaitEvent(st, e->cols_join, 0));
-	e->launches += 3;
+	e->launches += 2;
 	CU_CHECK(e, cudaGetLastError());
 	return 0;
 }
@@ -705,14 +693,15 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 			CREATE_CHECK(stream_setup<Plan512>());
 		if (const char *v = getenv("FOSPHOR_B200_FFT_VARIANT"))
 			e->fft_variant = atoi(v);
+		if (const char *v = getenv("FOSPHOR_B200_FFT_CTAS"))
+			e->fft_ctas_per_sm = atoi(v);
 	}
-	CREATE_CHECK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                                  (int)(sizeof(float2) * (size_t)(p.batch_max + 1))));
 	{
-		size_t upd = sizeof(float) * 2 * UPD_COLS * (size_t)((p.batch_max + ROWBLOCK - 1) / ROWBLOCK);
-		if (upd < UPD_SMEM_MAX)
-			upd = UPD_SMEM_MAX;
-		CREATE_CHECK(cudaFuncSetAttribute(update_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd));
+		size_t upd = sizeof(float2) * (size_t)(p.batch_max + 1);
+		const size_t parts = sizeof(float) * 2 * UPD_COLS * (size_t)((p.batch_max + ROWBLOCK - 1) / ROWBLOCK);
+		if (upd < parts) upd = parts;
+		if (upd < UPD_SMEM_MAX) upd = UPD_SMEM_MAX;
+		CREATE_CHECK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd));
 	}
 	CREATE_CHECK(cudaFuncSetAttribute(count_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                                  (int)(sizeof(unsigned) * 32 * k + sizeof(CountStage))));
