@@ -44,7 +44,7 @@ namespace fosphor_b200 {
 constexpr int ACC_COLS = 32;     /* columns per tile == warp width */
 constexpr int ACC_WARPS = 8;
 constexpr int ACC_THREADS = ACC_WARPS * 32;
-constexpr int UPD_THREADS = 128;
+constexpr int UPD_THREADS = 256;
 constexpr int REF_ROWS = 16;     /* display.cl:206-207 "sum / get_local_size(1)" */
 
 struct AccumArgs {
@@ -476,23 +476,23 @@ __device__ __forceinline__ void update_columns(const AccumArgs &a, int block, in
 		const size_t pbase = (size_t)c0 * blocks_per_call;
 		__syncthreads();                              /* previous group consumed */
 		{
-			/* thread (p0, c): partials p0, p0 + 8, ... of column c; 8 loads in flight */
+			/* thread (p0, c): partials p0, p0 + PSTEP, ... of column c; 2 x 8 loads in flight */
 			const int c = threadIdx.x % UPD_COLS, p0 = threadIdx.x / UPD_COLS;
 			constexpr int PSTEP = UPD_THREADS / UPD_COLS;
 			const bool okc = col0 + c < N;
 			const float *gl = a.part_live + pbase * N + col0 + c;
 			const float *gm = a.part_max + pbase * N + col0 + c;
-			for (int q0 = p0; q0 < nparts; q0 += 4 * PSTEP) {
-				float vl[4], vm[4];
+			for (int q0 = p0; q0 < nparts; q0 += 8 * PSTEP) {
+				float vl[8], vm[8];
 #pragma unroll
-				for (int u = 0; u < 4; u++) {
+				for (int u = 0; u < 8; u++) {
 					const int q = q0 + u * PSTEP;
 					const bool ok = okc && q < nparts;
 					vl[u] = ok ? __ldcg(gl + (size_t)q * N) : 0.0f;
 					vm[u] = ok ? __ldcg(gm + (size_t)q * N) : -1000.0f;
 				}
 #pragma unroll
-				for (int u = 0; u < 4; u++) {
+				for (int u = 0; u < 8; u++) {
 					const int q = q0 + u * PSTEP;
 					if (q < nparts) {
 						sh_part[q * UPD_COLS + c] = vl[u];
