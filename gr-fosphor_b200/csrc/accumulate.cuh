@@ -331,11 +331,6 @@ count_tma_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll
 				for (int r = 0; r < WARP_ROWS; r++)
 					pw[r] = rp[r * 32];
-				__syncwarp();                        /* the slot is consumed by every lane */
-				/* the slot was only READ through the generic proxy; program order after
-				 * the warp barrier is all the async-proxy overwrite needs */
-				if (lane == 0 && blk + TMA_DEPTH < nblocks)
-					issue(blk + TMA_DEPTH);
 #pragma unroll
 				for (int r = 0; r < WARP_ROWS; r++) {
 					live = fmaf(pw[r], __shfl_sync(0xffffffffu, wts, r), live);   /* display.cl:149-150 */
@@ -343,6 +338,13 @@ count_tma_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 					const unsigned off = bin_row_offset(pw[r], a.hofs, hscale2, kmax2);                /* :161-165 */
 					asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hits_addr + off) : "memory");     /* :170-177 */
 				}
+				/* Every lane has now USED its 16 values, so all shared loads of the slot
+				 * have completed; only then may the TMA engine overwrite it.  (Issuing
+				 * right after the loads were merely issued raced: the variant-equality
+				 * test caught a histogram mismatch once in a few runs.) */
+				__syncwarp();
+				if (lane == 0 && blk + TMA_DEPTH < nblocks)
+					issue(blk + TMA_DEPTH);
 			}
 			st.live[blk - g0][warp][lane] = live;
 			st.mx[blk - g0][warp][lane] = mx;
