@@ -250,6 +250,29 @@ cudaError_t stream_launch(fosphor_cu *e, const float2 *in, long long hop, int wf
 	return cudaGetLastError();
 }
 
+template <class P>
+cudaError_t cta_stream_setup()
+{
+	return cudaFuncSetAttribute(fft_power_cta_stream_kernel<P>,
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CtaStreamCfg<P>::SMEM);
+}
+
+template <class P>
+cudaError_t cta_stream_launch(fosphor_cu *e, const float2 *in, long long hop, int wf_pos, int n_spectra)
+{
+	using C = CtaStreamCfg<P>;
+	int grid = n_spectra;
+	const int resident = e->sm_count * C::CTAS_PER_SM;
+	if (grid > resident)
+		grid = resident;
+	prof_mark(e, 0, 0);
+	fft_power_cta_stream_kernel<P><<<grid, C::THREADS, C::SMEM, e->stream>>>(
+		in, hop, e->d_win, e->d_tw, e->d_wf, wf_pos, e->p.wf_rows - 1, n_spectra);
+	prof_mark(e, 0, 1);
+	e->launches++;
+	return cudaGetLastError();
+}
+
 cudaError_t launch_fft(fosphor_cu *e, const float2 *in, long long hop, int wf_pos, int n_spectra)
 {
 	/* TMA bulk copies need 16-byte aligned spectra */
@@ -259,6 +282,12 @@ cudaError_t launch_fft(fosphor_cu *e, const float2 *in, long long hop, int wf_po
 			return stream_launch<Plan1024>(e, in, hop, wf_pos, n_spectra);
 		if (e->p.fft_len == 512)
 			return stream_launch<Plan512>(e, in, hop, wf_pos, n_spectra);
+		if (e->p.fft_len == 2048)
+			return cta_stream_launch<Plan2048>(e, in, hop, wf_pos, n_spectra);
+		if (e->p.fft_len == 4096)
+			return cta_stream_launch<Plan4096>(e, in, hop, wf_pos, n_spectra);
+		if (e->p.fft_len == 8192)
+			return cta_stream_launch<Plan8192>(e, in, hop, wf_pos, n_spectra);
 	}
 	cudaError_t err = cudaErrorInvalidValue;
 	PLAN_SWITCH(e->p.fft_len, (err = plan_launch<P, false>(e, in, hop, wf_pos, nullptr, n_spectra)));
@@ -691,6 +720,12 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 			CREATE_CHECK(stream_setup<Plan1024>());
 		if (p.fft_len == 512)
 			CREATE_CHECK(stream_setup<Plan512>());
+		if (p.fft_len == 2048)
+			CREATE_CHECK(cta_stream_setup<Plan2048>());
+		if (p.fft_len == 4096)
+			CREATE_CHECK(cta_stream_setup<Plan4096>());
+		if (p.fft_len == 8192)
+			CREATE_CHECK(cta_stream_setup<Plan8192>());
 		if (const char *v = getenv("FOSPHOR_B200_FFT_VARIANT"))
 			e->fft_variant = atoi(v);
 		if (const char *v = getenv("FOSPHOR_B200_FFT_CTAS"))

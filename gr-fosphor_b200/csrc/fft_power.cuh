@@ -347,6 +347,138 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 	}
 }
 
+/* ------------------------------------------------------------------------ */
+/* Streaming variant for the three-pass plans (N = 2048, 4096, 8192)           */
+/* ------------------------------------------------------------------------ */
+/*
+ * One CTA per spectrum in flight, persistent CTAs striding over the spectra.
+ * Thread 0 asks the TMA engine for the NEXT spectrum (one cp.async.bulk of 8N
+ * bytes, mbarrier completion) into the second shared buffer while the CTA
+ * transforms the current one; the buffer that held the inputs becomes the padded
+ * exchange buffer of the same spectrum (pass-0 results wait in registers across
+ * one barrier so that no input is overwritten before it was read).  Same
+ * arithmetic as fft_power_kernel: bit-identical output.  N = 16384 does not
+ * fit two buffers in 227 KB and stays on the plain kernel.
+ */
+template <class P>
+struct CtaStreamCfg {
+	static_assert(P::NPASS == 3, "three-pass plans");
+	static constexpr int THREADS = P::T;
+	static constexpr int BF0 = P::NB0 / P::T;                     /* pass-0 butterflies per thread */
+	static_assert(BF0 * P::T == P::NB0, "pass 0 divides evenly");
+	static constexpr int BUF_ELEMS = P::SM_ELEMS;
+	static constexpr size_t SMEM = sizeof(float2) * (size_t)BUF_ELEMS * 2 + 16;
+	static constexpr unsigned IN_BYTES = sizeof(float2) * P::N;
+	static constexpr bool FITS = SMEM <= 200 * 1024;
+	static constexpr int CTAS_PER_SM = SMEM > 110 * 1024 ? 1 : (SMEM > 72 * 1024 ? 2 : (SMEM > 54 * 1024 ? 3 : 4));
+};
+
+template <class P>
+__global__ void __launch_bounds__(CtaStreamCfg<P>::THREADS, CtaStreamCfg<P>::CTAS_PER_SM)
+fft_power_cta_stream_kernel(const float2 *__restrict__ in, long long hop,
+                            const float *__restrict__ win, const float2 *__restrict__ tw,
+                            float *__restrict__ wf, int wf_pos, int wf_mask, int n_spectra)
+{
+	using C = CtaStreamCfg<P>;
+	constexpr int N = P::N, R0 = P::R0, R1 = P::R1;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float2 *bufs = reinterpret_cast<float2 *>(smem_raw);
+	const unsigned buf0 = smem_u32(bufs);
+	const unsigned bar0 = smem_u32(smem_raw + sizeof(float2) * (size_t)C::BUF_ELEMS * 2);
+	constexpr unsigned BUF_BYTES = sizeof(float2) * C::BUF_ELEMS;
+	const int tid = threadIdx.x;
+
+	if (tid == 0) {
+		mbar_init(bar0, 1);
+		mbar_init(bar0 + 8, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		if ((int)blockIdx.x < n_spectra) {
+			mbar_expect_tx(bar0, C::IN_BYTES);
+			bulk_g2s(buf0, in + (long long)blockIdx.x * hop, C::IN_BYTES, bar0);
+		}
+	}
+	__syncthreads();
+
+	unsigned phases = 0u;
+	int it = 0;
+	for (int s = blockIdx.x; s < n_spectra; s += gridDim.x, it++) {
+		const int b = it & 1;
+		float2 *buf = bufs + (size_t)b * C::BUF_ELEMS;
+
+		/* everybody is done with the other buffer (previous spectrum): refill it */
+		__syncthreads();
+		if (tid == 0 && s + (int)gridDim.x < n_spectra) {
+			const unsigned nb = (unsigned)(b ^ 1);
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			mbar_expect_tx(bar0 + 8 * nb, C::IN_BYTES);
+			bulk_g2s(buf0 + nb * BUF_BYTES, in + (long long)(s + gridDim.x) * hop, C::IN_BYTES, bar0 + 8 * nb);
+		}
+		while (!mbar_try_wait(bar0 + 8 * b, (phases >> b) & 1u)) { }
+		phases ^= 1u << b;
+
+		float *row = wf + (size_t)((wf_pos + s) & wf_mask) * N;
+
+		/* ---- pass 0: inputs from shared memory, results parked in registers ---- */
+		float2 v0[C::BF0][R0];
+#pragma unroll
+		for (int q = 0; q < C::BF0; q++) {
+			const int i = tid + q * P::T;
+#pragma unroll
+			for (int t = 0; t < R0; t++) {
+				const float2 x = buf[i + t * P::NB0];
+				const float w = __ldg(&win[i + t * P::NB0]);
+				v0[q][t] = make_float2(x.x * w, x.y * w);           /* fft.cl:416-417 */
+			}
+			dif<R0>(v0[q]);
+		}
+		__syncthreads();                        /* all inputs consumed: buf becomes the exchange */
+#pragma unroll
+		for (int q = 0; q < C::BF0; q++) {
+			const int i = tid + q * P::T;
+			static_for<0, R0>([&](auto tc) {
+				constexpr int t = decltype(tc)::value;
+				buf[pad_idx<P>(i * R0 + t)] = v0[q][brev<R0>(t)];
+			});
+		}
+		__syncthreads();
+
+		/* ---- pass 1 (P = R0) ---- */
+		const int i = tid;
+		const int k = i & (R0 - 1);
+		float2 v[R1];
+#pragma unroll
+		for (int t = 0; t < R1; t++)
+			v[t] = buf[pad_idx<P>(i + t * P::NB1)];
+#pragma unroll
+		for (int t = 1; t < R1; t++)
+			v[t] = cmul(v[t], __ldg(&tw[t * R0 + k]));
+		dif<R1>(v);
+		const int j = (i - k) * R1 + k;
+		__syncthreads();
+		static_for<0, R1>([&](auto tc) {
+			constexpr int t = decltype(tc)::value;
+			buf[pad_idx<P>(j + t * R0)] = v[brev<R1>(t)];
+		});
+		__syncthreads();
+
+		/* ---- pass 2 (P = R0 * R1), last ---- */
+		constexpr int P2 = R0 * R1;
+		const int k2 = i & (P2 - 1);
+#pragma unroll
+		for (int t = 0; t < R1; t++)
+			v[t] = buf[pad_idx<P>(i + t * P::NB1)];
+#pragma unroll
+		for (int t = 1; t < R1; t++)
+			v[t] = cmul(v[t], __ldg(&tw[P::TW1 + t * P2 + k2]));
+		dif<R1>(v);
+		static_for<0, R1>([&](auto tc) {
+			constexpr int t = decltype(tc)::value;
+			row[i + t * P::NB1] = log_power(v[brev<R1>(t)]);
+		});
+	}
+}
+
 /* The supported sizes (BASELINE.json configs[4] sweep) */
 using Plan512   = FftPlan<512,   16, 32, 2>;
 using Plan1024  = FftPlan<1024,  32, 32, 2>;

@@ -256,12 +256,13 @@ def test_fallback_paths_odd_batches_and_unaligned_hop(torch_cuda):
 
 
 def test_kernel_variants_are_bit_identical(torch_cuda, monkeypatch):
-    """TMA-prefetching FFT kernel vs plain, TMA-staged count kernel vs plain,
-    two-stream overlap vs one stream: same arithmetic, bit-identical waterfall /
-    histogram / spectrum (N = 1024 and 512, several calls folded per launch)."""
+    """TMA-prefetching FFT kernels (warp-level for N = 512/1024, CTA-level for
+    2048/4096/8192) vs plain, TMA-staged count kernel vs plain, two-stream overlap
+    vs one stream: same arithmetic, bit-identical waterfall / histogram / spectrum
+    (several calls folded per launch)."""
     torch = torch_cuda
-    for n in (1024, 512):
-        calls, b = 5, 1024
+    for n in (1024, 512, 2048, 4096, 8192):
+        calls, b = (5, 1024) if n <= 1024 else (3, 256)
         x = signals.noise_tones(n * b * calls, n_fft=n, seed=77)
         d = _to_dev(torch, x)
         outs = []
