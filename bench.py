@@ -37,7 +37,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 N_FFT, N_BINS, OVERLAP, BATCH, CALLS_PER_STEP = 1024, 256, 4, 1024, 384
-WF_ROWS = 32768  # device waterfall ring: the FFT pass is launched once per 16-32 calls
+WF_ROWS = 32768  # device waterfall ring: the FFT pass is launched once per 32 calls (the two-stream pass uses 2x)
 REF_CALLS_PER_STEP = 8   # reference arm: one sink frame (base_sink_c_impl.cc:133-146) per step
 
 
@@ -183,7 +183,21 @@ def run_b200(args):
     hop = n // OVERLAP
 
     wf_rows = args.wf_rows
-    eng = Fosphor(fft_len=n, n_bins=k, wf_rows=wf_rows, device=local, stream=stream.cuda_stream)
+
+    def make_engine(rows, overlap):
+        """overlap False: every kernel on one stream (clean per-kernel timing);
+        True: count/update of one chunk beside the FFT of the next (needs 2 chunks of ring)."""
+        old = os.environ.get("FOSPHOR_B200_OVERLAP")
+        os.environ["FOSPHOR_B200_OVERLAP"] = "1" if overlap else "0"
+        try:
+            return Fosphor(fft_len=n, n_bins=k, wf_rows=rows, device=local, stream=stream.cuda_stream)
+        finally:
+            if old is None:
+                os.environ.pop("FOSPHOR_B200_OVERLAP")
+            else:
+                os.environ["FOSPHOR_B200_OVERLAP"] = old
+
+    eng = make_engine(wf_rows, False)
 
     # ---- inputs: two distinct seconds of signal, raw and pre-overlapped (3.2 GB each >> L2) ----
     pool_n = raw_pool_n = 2
@@ -257,28 +271,24 @@ def run_b200(args):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
 
-    # the same kernels timed without the count/update overlap (one stream), for reference
-    old_ov = os.environ.get("FOSPHOR_B200_OVERLAP")
-    os.environ["FOSPHOR_B200_OVERLAP"] = "0"
-    eng_iso = Fosphor(fft_len=n, n_bins=k, wf_rows=wf_rows, device=local, stream=stream.cuda_stream)
-    if old_ov is None:
-        os.environ.pop("FOSPHOR_B200_OVERLAP")
-    else:
-        os.environ["FOSPHOR_B200_OVERLAP"] = old_ov
-    eng, eng_iso = eng_iso, eng
-    ms_iso = timed(lambda i: step_device(i, True), prof_steps, 2)
+    # ---- two-stream mode: count/update of chunk c beside the FFT of chunk c+1 (ring of 2 chunks) ----
+    eng_one = eng
+    eng = make_engine(2 * wf_rows, True)
+    ms_two = timed(lambda i: step_device(i, True), args.steps, args.warmup)
     eng.profile(True)
     timed(lambda i: step_device(i, True), prof_steps, 0)
-    prof_iso = eng.profile_read()
+    prof_two = eng.profile_read()
     eng.profile(False)
+    two = {"value": world * args.steps * samples_per_step / (ms_two * 1e-3) / 1e6,
+           "unit": "Mcomplex-samples/s", "ms_per_step": ms_two / args.steps, "wf_rows": 2 * wf_rows,
+           "step_frac": step_bytes / (ms_two / args.steps * 1e-3) / 1e9 / peak,
+           "fft_ms_per_launch_concurrent": prof_two["fft_ms"] / max(1, prof_two["fft_launches"]),
+           "count_ms_per_launch_concurrent": prof_two["count_ms"] / max(1, prof_two["count_launches"]),
+           "update_ms_per_launch_concurrent": prof_two["update_ms"] / max(1, prof_two["update_launches"]),
+           "note": "engine default when the ring holds two chunks: FFT kernel at 2 CTAs/SM, count/update "
+                   "co-resident on a second stream"}
     eng.close()
-    eng = eng_iso
-    iso = {"ms_per_step": ms_iso / prof_steps,
-           "fft_ms_per_launch": prof_iso["fft_ms"] / max(1, prof_iso["fft_launches"]),
-           "count_ms_per_launch": prof_iso["count_ms"] / max(1, prof_iso["count_launches"]),
-           "update_ms_per_launch": prof_iso["update_ms"] / max(1, prof_iso["update_launches"]),
-           "fft_GBps": fft_kernel_bytes(n, spectra_per_step * prof_steps // max(1, prof_iso["fft_launches"]), 1.0)
-           / (prof_iso["fft_ms"] / max(1, prof_iso["fft_launches"]) * 1e-3) / 1e9}
+    eng = eng_one
 
     # ---- in-engine overlap variant (raw stream, hop = N/4) ----
     ms_hop = timed(lambda i: step_device(i, False), args.steps, args.warmup)
@@ -336,7 +346,7 @@ def run_b200(args):
     del pool, raws
     torch.cuda.empty_cache()
     eng_dev = eng
-    eng = Fosphor(fft_len=n, n_bins=k, wf_rows=1024, device=local, stream=stream.cuda_stream)   # reference-sized ring
+    eng = make_engine(1024, False)   # reference-sized ring
     ms_e2e = timed_host(step_e2e, e2e_steps, 1)
     e2e = world * e2e_steps * samples_per_step / (ms_e2e * 1e-3) / 1e6
     ms_e2e_raw = timed_host(step_e2e_raw, e2e_steps, 1)
@@ -364,18 +374,18 @@ def run_b200(args):
                        "multi_gpu": "one channel per GPU, NCCL max all-reduce of max-hold per step" if world > 1 else "single"},
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "fft_power_kernel<Plan1024>",
+            "roofline": {"bound": "hbm", "kernel": "fft_power_stream_kernel<Plan1024, TWREG> (one-stream pass: per-kernel timing not disturbed by a co-running kernel)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic,
                          "bytes_per_launch": fft_bytes, "ms_per_launch": fft_ms,
                          "spectra_per_launch": spectra_per_fft_launch,
                          "count_ms_per_launch": count_ms, "update_ms_per_launch": update_ms,
-                         "single_stream": iso,
                          "step_algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                          "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e, "unit": "Mcomplex-samples/s",
                     "h2d_bytes_per_step": 8 * samples_per_step, "d2h_bytes_per_step": d2h,
                     "api": "fosphor_cu_process_host x384 + fosphor_cu_finish (page-locked host pre-overlapped stream)"},
+            "two_stream_overlap": two,
             "overlap_in_engine": {"value": value_hop, "e2e": e2e_raw, "unit": "Mcomplex-samples/s",
                                   "h2d_bytes_per_step": 8 * raw_len,
                                   "note": "raw stream, hop=N/4 addressing inside the FFT kernel (r=1/4)"},

@@ -60,12 +60,15 @@ struct fosphor_cu {
 	cudaEvent_t cnt_done[2] = {nullptr, nullptr};
 	cudaEvent_t acc_done = nullptr;
 	cudaEvent_t cols_fork = nullptr, cols_join = nullptr;   /* column update runs beside the cell update */
-	int overlap = 0;                     /* env FOSPHOR_B200_OVERLAP=1: count/update of chunk c on a second
-	                                      * stream while the FFT of chunk c+1 runs.  Off by default: the FFT
-	                                      * kernel fills every SM's registers and shared memory, so nothing
-	                                      * co-resides with it and halving the chunks only costs (measured). */
-	int fft_ctas_per_sm = 0;             /* env FOSPHOR_B200_FFT_CTAS: leave room beside the persistent FFT
-	                                      * kernel (e.g. 2) so count CTAs can co-reside in overlap mode */
+	int overlap = 1;                     /* env FOSPHOR_B200_OVERLAP: 1 = count/update of chunk c run on a second
+	                                      * stream while the FFT of chunk c+1 runs (needs a ring of >= 2 chunks).
+	                                      * The persistent FFT kernel then takes 2 CTAs per SM instead of 3 so
+	                                      * that count CTAs can co-reside: the FFT is HBM bound and barely
+	                                      * slower with 8 warps/SM (measured 67.8 vs 66.4 us), count is issue
+	                                      * bound - together +11 % on the bench step.  0 = one stream. */
+	bool two_streams_now = false;        /* set per process call */
+	int fft_ctas_per_sm = 0;             /* env FOSPHOR_B200_FFT_CTAS: force the CTAs/SM of the persistent FFT
+	                                      * kernel (0 = automatic: 3, or 2 when count runs beside it) */
 	CUtensorMap wf_tmap;                 /* waterfall ring as a 2-D tensor, box = 16 rows x 32 columns */
 	bool tmap_ok = false;
 	int count_variant = 1;               /* 1: TMA-staged count kernel where applicable, 0: plain
@@ -234,8 +237,12 @@ cudaError_t stream_launch(fosphor_cu *e, const float2 *in, long long hop, int wf
 {
 	using C = StreamCfg<P>;
 	int grid = (n_spectra + C::WARPS - 1) / C::WARPS;
-	const int resident = e->sm_count * (e->fft_ctas_per_sm > 0 && e->fft_ctas_per_sm < C::CTAS_PER_SM
-	                                        ? e->fft_ctas_per_sm : C::CTAS_PER_SM);
+	int per_sm = C::CTAS_PER_SM;
+	if (e->fft_ctas_per_sm > 0 && e->fft_ctas_per_sm < per_sm)
+		per_sm = e->fft_ctas_per_sm;
+	else if (e->fft_ctas_per_sm == 0 && e->two_streams_now && per_sm > 2)
+		per_sm = 2;                      /* leave room for the count kernel on the other stream */
+	const int resident = e->sm_count * per_sm;
 	if (grid > resident)
 		grid = resident;                 /* persistent warps, grid-stride over spectra */
 	prof_mark(e, 0, 0);
@@ -480,6 +487,7 @@ int process_device_calls(fosphor_cu *e, const float2 *in, int n_calls, int batch
 		const bool two_streams = e->overlap && ring_calls >= 2 && n_calls > ring_calls / 2;
 		if (two_streams)
 			calls_per_chunk = ring_calls / 2;
+		e->two_streams_now = two_streams;
 		if (calls_per_chunk > e->max_slices)
 			calls_per_chunk = e->max_slices;
 		cudaStream_t acc = two_streams ? e->acc_stream : e->stream;
