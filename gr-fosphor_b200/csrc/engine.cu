@@ -60,7 +60,10 @@ struct fosphor_cu {
 	cudaEvent_t cnt_done[2] = {nullptr, nullptr};
 	cudaEvent_t acc_done = nullptr;
 	cudaEvent_t cols_fork = nullptr, cols_join = nullptr;   /* column update runs beside the cell update */
-	int overlap = 1;                     /* env FOSPHOR_B200_OVERLAP: 1 = count/update of chunk c run on a second
+	int overlap = -1;                    /* env FOSPHOR_B200_OVERLAP: -1 (default) = automatic: on for the N = 512 /
+	                                      * 1024 persistent FFT kernel, off for the other plans (their FFT kernels fill
+	                                      * the SMs' shared memory, nothing can co-reside and halving the chunks only
+	                                      * costs); 1 = count/update of chunk c run on a second
 	                                      * stream while the FFT of chunk c+1 runs (needs a ring of >= 2 chunks).
 	                                      * The persistent FFT kernel then takes 2 CTAs per SM instead of 3 so
 	                                      * that count CTAs can co-reside: the FFT is HBM bound and barely
@@ -484,7 +487,10 @@ int process_device_calls(fosphor_cu *e, const float2 *in, int n_calls, int batch
 		 * chunk c+1 (main stream). */
 		const int ring_calls = e->p.wf_rows / batch;         /* >= 1: wf_rows >= batch_max */
 		int calls_per_chunk = ring_calls;
-		const bool two_streams = e->overlap && ring_calls >= 2 && n_calls > ring_calls / 2;
+		const bool auto_on = (e->p.fft_len == 1024 || e->p.fft_len == 512) && e->fft_variant != 0 &&
+		                     (hop & 1) == 0 && (reinterpret_cast<unsigned long long>(in) & 15ull) == 0;
+		const bool want = e->overlap > 0 || (e->overlap < 0 && auto_on);
+		const bool two_streams = want && ring_calls >= 2 && n_calls > ring_calls / 2;
 		if (two_streams)
 			calls_per_chunk = ring_calls / 2;
 		e->two_streams_now = two_streams;

@@ -23,6 +23,23 @@ def alg_bytes_per_call(n, k, b, r):
 
 
 def run(torch, name, n, k, overlap, b, calls, wf_rows, in_engine_overlap, **kw):
+    """best of the engine's two scheduling modes (one stream / two-stream overlap)"""
+    best = None
+    for mode in ("0", "1"):
+        os.environ["FOSPHOR_B200_OVERLAP"] = mode
+        r = run_one(torch, name, n, k, overlap, b, calls, wf_rows, in_engine_overlap, **kw)
+        r["two_stream_overlap"] = mode == "1"
+        if best is None or r["Msamples_per_s"] > best["Msamples_per_s"]:
+            other = best
+            best = r
+        else:
+            other = r
+    os.environ.pop("FOSPHOR_B200_OVERLAP")
+    best["other_mode_Msamples_per_s"] = other["Msamples_per_s"] if other else None
+    return best
+
+
+def run_one(torch, name, n, k, overlap, b, calls, wf_rows, in_engine_overlap, **kw):
     from gr_fosphor_b200.engine import Fosphor
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device=dev)
