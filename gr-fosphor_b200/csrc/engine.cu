@@ -107,7 +107,8 @@ struct fosphor_cu {
 	unsigned long long launches = 0;
 	int fft_variant = 2;                 /* env FOSPHOR_B200_FFT_VARIANT, N = 512/1024 with aligned input:
 	                                      * 2: TMA-prefetching persistent kernel, twiddles in registers
-	                                      * 1: same, twiddles fetched per spectrum   0: plain kernel */
+	                                      * 1: same, twiddles fetched per spectrum   0: plain kernel
+	                                      * 3: as 2, plus the CTA-level streaming kernel for N = 2048..8192 */
 
 	/* optional per-kernel timing (bench.py roofline): event pairs around launches */
 	bool profiling = false;
@@ -249,7 +250,7 @@ cudaError_t stream_launch(fosphor_cu *e, const float2 *in, long long hop, int wf
 	if (grid > resident)
 		grid = resident;                 /* persistent warps, grid-stride over spectra */
 	prof_mark(e, 0, 0);
-	if (e->fft_variant == 2)
+	if (e->fft_variant >= 2)
 		fft_power_stream_kernel<P, true><<<grid, C::THREADS, C::SMEM_TWREG, e->stream>>>(
 			in, hop, e->d_win, e->d_tw, e->d_wf, wf_pos, e->p.wf_rows - 1, n_spectra);
 	else
@@ -288,16 +289,24 @@ cudaError_t launch_fft(fosphor_cu *e, const float2 *in, long long hop, int wf_po
 	/* TMA bulk copies need 16-byte aligned spectra */
 	const bool aligned = ((reinterpret_cast<unsigned long long>(in) & 15ull) == 0) && ((hop & 1) == 0);
 	if (aligned && e->fft_variant != 0) {
+		if (e->p.fft_len == 1024 || e->p.fft_len == 512) {
+			/* variant 3 means "2 + experiments" for these sizes */
+		}
 		if (e->p.fft_len == 1024)
 			return stream_launch<Plan1024>(e, in, hop, wf_pos, n_spectra);
 		if (e->p.fft_len == 512)
 			return stream_launch<Plan512>(e, in, hop, wf_pos, n_spectra);
-		if (e->p.fft_len == 2048)
-			return cta_stream_launch<Plan2048>(e, in, hop, wf_pos, n_spectra);
-		if (e->p.fft_len == 4096)
-			return cta_stream_launch<Plan4096>(e, in, hop, wf_pos, n_spectra);
-		if (e->p.fft_len == 8192)
-			return cta_stream_launch<Plan8192>(e, in, hop, wf_pos, n_spectra);
+		/* The CTA-level streaming kernel measured SLOWER than the plain one (N = 4096:
+		 * 101 vs 86 us per 8192 spectra; fewer resident CTAs outweigh the prefetch), so
+		 * it is only reachable as experiment variant 3. */
+		if (e->fft_variant == 3) {
+			if (e->p.fft_len == 2048)
+				return cta_stream_launch<Plan2048>(e, in, hop, wf_pos, n_spectra);
+			if (e->p.fft_len == 4096)
+				return cta_stream_launch<Plan4096>(e, in, hop, wf_pos, n_spectra);
+			if (e->p.fft_len == 8192)
+				return cta_stream_launch<Plan8192>(e, in, hop, wf_pos, n_spectra);
+		}
 	}
 	cudaError_t err = cudaErrorInvalidValue;
 	PLAN_SWITCH(e->p.fft_len, (err = plan_launch<P, false>(e, in, hop, wf_pos, nullptr, n_spectra)));

@@ -266,7 +266,7 @@ def test_kernel_variants_are_bit_identical(torch_cuda, monkeypatch):
         x = signals.noise_tones(n * b * calls, n_fft=n, seed=77)
         d = _to_dev(torch, x)
         outs = []
-        for fftv, cntv, ov in (("2", "1", "1"), ("0", "0", "0"), ("1", "0", "1"), ("0", "1", "0")):
+        for fftv, cntv, ov in (("2", "1", "1"), ("0", "0", "0"), ("1", "0", "1"), ("3", "1", "0")):
             monkeypatch.setenv("FOSPHOR_B200_FFT_VARIANT", fftv)
             monkeypatch.setenv("FOSPHOR_B200_COUNT_VARIANT", cntv)
             monkeypatch.setenv("FOSPHOR_B200_OVERLAP", ov)
