@@ -37,7 +37,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 N_FFT, N_BINS, OVERLAP, BATCH, CALLS_PER_STEP = 1024, 256, 4, 1024, 384
-WF_ROWS = 32768  # device waterfall ring: the FFT pass is launched once per 32 calls (the two-stream pass uses 2x)
+WF_ROWS = 65536  # device waterfall ring: one FFT + one accumulate launch per 64 calls (per-launch ramp/tail ~8 us)
 REF_CALLS_PER_STEP = 8   # reference arm: one sink frame (base_sink_c_impl.cc:133-146) per step
 
 
@@ -271,22 +271,22 @@ def run_b200(args):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
 
-    # ---- two-stream mode: count/update of chunk c beside the FFT of chunk c+1 (ring of 2 chunks) ----
+    # ---- two-stream mode: accumulate of chunk c beside the FFT of chunk c+1 (same ring, two chunks) ----
     eng_one = eng
-    eng = make_engine(2 * wf_rows, True)
+    eng = make_engine(wf_rows, True)
     ms_two = timed(lambda i: step_device(i, True), args.steps, args.warmup)
     eng.profile(True)
     timed(lambda i: step_device(i, True), prof_steps, 0)
     prof_two = eng.profile_read()
     eng.profile(False)
     two = {"value": world * args.steps * samples_per_step / (ms_two * 1e-3) / 1e6,
-           "unit": "Mcomplex-samples/s", "ms_per_step": ms_two / args.steps, "wf_rows": 2 * wf_rows,
+           "unit": "Mcomplex-samples/s", "ms_per_step": ms_two / args.steps, "wf_rows": wf_rows,
            "step_frac": step_bytes / (ms_two / args.steps * 1e-3) / 1e9 / peak,
            "fft_ms_per_launch_concurrent": prof_two["fft_ms"] / max(1, prof_two["fft_launches"]),
-           "count_ms_per_launch_concurrent": prof_two["count_ms"] / max(1, prof_two["count_launches"]),
-           "update_ms_per_launch_concurrent": prof_two["update_ms"] / max(1, prof_two["update_launches"]),
-           "note": "engine default when the ring holds two chunks: FFT kernel at 2 CTAs/SM, count/update "
-                   "co-resident on a second stream"}
+           "accumulate_ms_per_launch_concurrent": prof_two["count_ms"] / max(1, prof_two["count_launches"]) +
+           prof_two["update_ms"] / max(1, prof_two["update_launches"]),
+           "note": "FOSPHOR_B200_OVERLAP=1 (not the default): accumulate kernel of one half-ring chunk on a second "
+                   "stream beside the FFT of the next; both slow down in proportion, see DESIGN.md"}
     eng.close()
     eng = eng_one
 
@@ -374,12 +374,13 @@ def run_b200(args):
                        "multi_gpu": "one channel per GPU, NCCL max all-reduce of max-hold per step" if world > 1 else "single"},
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "fft_power_stream_kernel<Plan1024, TWREG> (one-stream pass: per-kernel timing not disturbed by a co-running kernel)",
+            "roofline": {"bound": "hbm", "kernel": "fft_power_stream_kernel<Plan1024, TWREG>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic,
                          "bytes_per_launch": fft_bytes, "ms_per_launch": fft_ms,
                          "spectra_per_launch": spectra_per_fft_launch,
-                         "count_ms_per_launch": count_ms, "update_ms_per_launch": update_ms,
+                         "accumulate_kernel": "accumulate_fused_kernel<8,16,4,64,TMA> (count + rise/decay + live + max-hold, one launch)",
+                         "accumulate_ms_per_launch": count_ms + update_ms,
                          "step_algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                          "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e, "unit": "Mcomplex-samples/s",

@@ -543,6 +543,383 @@ update_kernel(const AccumArgs a, int cell_blocks, int cap)
 		update_columns(a, (int)blockIdx.x - cell_blocks, cap, reinterpret_cast<float *>(upd_smem));
 }
 
+/* ------------------------------------------------------------------------ */
+/* Fused accumulate kernel: count + rise/decay + live IIR + max-hold            */
+/* ------------------------------------------------------------------------ */
+/*
+ * One CTA owns COLS adjacent frequency columns for the whole launch and walks
+ * the calls of the chunk in order, so the per-cell recurrence along the call
+ * axis (display.cl:241-247) never leaves the SM: the COLS x K histogram cells
+ * of the tile live in shared memory from the first call to the last, the hit
+ * counts of a call are built and consumed in shared memory, and the only
+ * global traffic is the log-power rows (read once, through the TMA engine) and
+ * one read + one write of the tile's state per LAUNCH.  (The split count /
+ * update kernels above move a u16 count plane per slice through HBM and spend
+ * their issue slots on that bookkeeping.)
+ *
+ * Warp roles.  FW "counter" warps turn rows into hit counts and live/max
+ * partials; UW "updater" warps apply the rise/decay step and the live / max
+ * recurrences of call c while the counters are already busy with call c+1.
+ * Hit tile and partials are double buffered by call parity; the two roles
+ * meet only through mbarriers (cnt_done[par]: counters -> updaters,
+ * hits_free[par]: updaters -> counters), never through a block barrier, so no
+ * counter warp ever waits for another counter warp.
+ *
+ * Geometry: a warp step is 32/COLS consecutive rows x COLS columns.  The rows
+ * of a call are dealt to ACC_VW = 16 "virtual warps" in contiguous runs of
+ * Rv = 16 * ceil(B/16 / 16) rows; counter warp w takes virtual warps w,
+ * w+FW, ...  A run is fetched in boxes of BOXR rows x COLS columns by the TMA
+ * engine (2-D tensor map), each counter warp running its own ring of
+ * ACC_DEPTH boxes that keeps going across call boundaries.  hits[bin][col]
+ * holds plain totals: the rows of one step meet in it through shared-memory
+ * atomics (a bank conflict costs a wavefront in the LSU, not an issue slot,
+ * and the kernel is issue bound).
+ *
+ * Live-spectrum sums: lane (r, col) adds the rows of its virtual warp in row
+ * order, the 16 virtual-warp partials are added in order, the 32/COLS row
+ * groups by an xor butterfly - a fixed order that depends on (B, COLS) only,
+ * not on FW, BOXR, the load path or how calls are folded into launches.
+ *
+ * TMA = false: same arithmetic with plain loads (BOXR = 16, rows past the
+ * batch masked), for batches / ring positions that do not align to a box.
+ */
+constexpr int ACC_VW = 16;        /* virtual warps: the unit of the row -> lane assignment */
+constexpr int ACC_DEPTH = 3;      /* TMA boxes in flight per counter warp */
+constexpr int ACC_WSM_MAX = 4096; /* TMA path: live weights of the batch staged in shared memory */
+
+template <int COLS>
+__device__ __forceinline__ unsigned bin_cell_offset(float pwr, float hofs, float hscale2, int kmax2)
+{
+	/* see bin_row_offset(): byte offset of hits[bin][0] with COLS u32 per bin */
+	const int i = __float2int_rd(__fmul_rn(hscale2, __fadd_rn(pwr, hofs)));
+	const int j = min(max(i, -1), kmax2) + 1;        /* 0 .. 2*kmax + 1 */
+	return ((unsigned)j & ~1u) * (COLS * 2);         /* (j >> 1) * COLS * 4 */
+}
+
+/* rows per virtual warp and call */
+__host__ __device__ inline int acc_rows_per_vwarp(int batch)
+{
+	const int units = (batch + 15) / 16;
+	return 16 * ((units + ACC_VW - 1) / ACC_VW);
+}
+
+__device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned parity)
+{
+	unsigned ok;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+		             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		             "selp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+	} while (!ok);
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int COLS, int FW, int UW, int BOXR>
+struct FusedCfg {
+	static_assert(COLS == 4 || COLS == 8 || COLS == 16 || COLS == 32, "tile width");
+	static_assert(BOXR % 16 == 0 && BOXR <= 256, "box rows");
+	static_assert(ACC_VW % FW == 0, "counter warps divide the virtual ones");
+	static constexpr int RG = 32 / COLS;                 /* rows per warp step */
+	static constexpr int STEPS = BOXR / RG;              /* steps per box */
+	static constexpr int VPW = ACC_VW / FW;              /* virtual warps per counter warp */
+	static constexpr int THREADS = (FW + UW) * 32;
+	static constexpr size_t BOX_BYTES = sizeof(float) * BOXR * COLS;
+	static constexpr size_t STAGE_BYTES = BOX_BYTES * ACC_DEPTH * FW;
+	static constexpr size_t BAR_BYTES = 512;             /* FW * ACC_DEPTH TMA barriers + 4 role barriers */
+	static_assert(8 * (ACC_DEPTH * FW + 4) <= BAR_BYTES, "barrier area");
+	static constexpr size_t PART_BYTES = sizeof(float) * 2 * 2 * ACC_VW * 32;
+	static size_t smem(int K, int batch, bool tma)
+	{
+		return (tma ? STAGE_BYTES + sizeof(float) * (size_t)((batch + 3) & ~3) + sizeof(float2) * (size_t)(batch + 1) : 0) +
+		       BAR_BYTES + PART_BYTES + sizeof(float) * 3 * (size_t)K * COLS + 128;
+	}
+};
+
+template <int COLS, int FW, int UW, int BOXR, bool TMA>
+__global__ void __launch_bounds__((FW + UW) * 32, 1)
+accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
+{
+	using C = FusedCfg<COLS, FW, UW, BOXR>;
+	constexpr int RG = C::RG, STEPS = C::STEPS, VPW = C::VPW;
+	extern __shared__ __align__(128) unsigned char fz_smem[];
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int col0 = blockIdx.x * COLS;
+	const int K = a.n_bins, N = a.n, B = a.batch;
+	const int cells = K * COLS;
+
+	/* carve shared memory */
+	unsigned char *sp = fz_smem;
+	float *stage = reinterpret_cast<float *>(sp);
+	if (TMA) sp += C::STAGE_BYTES;
+	unsigned long long *bars = reinterpret_cast<unsigned long long *>(sp);
+	sp += C::BAR_BYTES;
+	float *parts = reinterpret_cast<float *>(sp);        /* [2 parity][2 live/max][ACC_VW][32] */
+	sp += C::PART_BYTES;
+	unsigned *hits = reinterpret_cast<unsigned *>(sp);   /* [2 parity][K][COLS] */
+	sp += sizeof(unsigned) * 2 * (size_t)cells;
+	float *hist_s = reinterpret_cast<float *>(sp);       /* [K][COLS] */
+	sp += sizeof(float) * (size_t)cells;
+	float *wsm = reinterpret_cast<float *>(sp);          /* [B] live weights (TMA path: B <= ACC_WSM_MAX) */
+	sp += sizeof(float) * (size_t)((B + 3) & ~3);
+	float2 *lut_s = reinterpret_cast<float2 *>(sp);      /* [B+1] (d, e) table (TMA path) */
+
+	const unsigned role_bar = cnt_smem_u32(bars + ACC_DEPTH * FW);   /* cnt_done[0,1], hits_free[0,1] */
+
+	if (threadIdx.x == 0) {
+		for (int i = 0; i < ACC_DEPTH * FW; i++)
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cnt_smem_u32(bars + i)));
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar), "r"(FW));
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar + 8), "r"(FW));
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar + 16), "r"(UW));
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar + 24), "r"(UW));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	/* tile state in, hit tiles cleared, weights staged */
+	{
+		constexpr int cpr = COLS / 4;                /* float4 groups per bin row */
+		float4 *h4 = reinterpret_cast<float4 *>(hist_s);
+		uint4 *z4 = reinterpret_cast<uint4 *>(hits);
+		for (int g = threadIdx.x; g < cells / 4; g += C::THREADS) {
+			const int bin = g / cpr, c4 = (g % cpr) * 4;
+			h4[g] = *reinterpret_cast<const float4 *>(a.hist + (size_t)bin * N + col0 + c4);
+			z4[g] = make_uint4(0u, 0u, 0u, 0u);
+			z4[g + cells / 4] = make_uint4(0u, 0u, 0u, 0u);
+		}
+		if (TMA) {
+			for (int i = threadIdx.x; i < B; i += C::THREADS)
+				wsm[i] = __ldg(&a.weights[i]);
+			for (int i = threadIdx.x; i <= B; i += C::THREADS)
+				lut_s[i] = __ldg(&a.lut[i]);
+		}
+	}
+	__syncthreads();
+
+	if (warp < FW) {
+		/* ================= counter warps ================= */
+		const int r = lane / COLS, cc = lane % COLS;
+		const int Rv = acc_rows_per_vwarp(B);
+		const unsigned mask = (unsigned)a.wf_mask;
+		const unsigned bar0 = cnt_smem_u32(bars + warp * ACC_DEPTH);
+		const unsigned stage0 = cnt_smem_u32(stage) + (unsigned)(warp * ACC_DEPTH * C::BOX_BYTES);
+
+		/* boxes of my j-th virtual warp in one call (TMA: all runs are whole boxes) */
+		int nbv[VPW];
+#pragma unroll
+		for (int j = 0; j < VPW; j++) {
+			const int lo = (warp + FW * j) * Rv;
+			nbv[j] = lo < B ? (min(B, lo + Rv) - lo + BOXR - 1) / BOXR : 0;
+		}
+		int per_call = 0;
+#pragma unroll
+		for (int j = 0; j < VPW; j++)
+			per_call += nbv[j];
+
+		/* issue side of my TMA ring (lane 0 only): next box to request = box iss_t of call iss_call */
+		static_assert(VPW <= 2, "issue() handles one or two runs per counter warp");
+		int iss_call = per_call > 0 ? 0 : a.n_calls, iss_t = 0;
+		unsigned iss_slot = 0;
+		auto issue = [&]() {
+			if (iss_call < a.n_calls) {
+				const bool second = VPW > 1 && iss_t >= nbv[0];
+				const int v = second ? warp + FW : warp;
+				const int k = second ? iss_t - nbv[0] : iss_t;
+				const unsigned row = ((unsigned)a.wf_pos + (unsigned)iss_call * (unsigned)B +
+				                      (unsigned)(v * Rv + k * BOXR)) & mask;
+				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+				             ::"r"(bar0 + 8u * iss_slot), "r"((unsigned)C::BOX_BYTES) : "memory");
+				tma_load_2d(stage0 + iss_slot * (unsigned)C::BOX_BYTES, &tmap, col0, (int)row, bar0 + 8u * iss_slot);
+				iss_slot = iss_slot + 1 == ACC_DEPTH ? 0 : iss_slot + 1;
+				if (++iss_t == per_call) {
+					iss_t = 0;
+					iss_call++;
+				}
+			}
+		};
+
+		if (TMA && lane == 0) {
+#pragma unroll 1
+			for (int d = 0; d < ACC_DEPTH; d++)
+				issue();
+		}
+
+		const int kmax2 = 2 * (K - 1);
+		const float hscale2 = 2.0f * a.hscale;
+		const float hofs = a.hofs;
+		const float *wcol = a.wf + col0 + cc;
+		unsigned slot = 0, phase = 0u;
+
+		for (int call = 0; call < a.n_calls; call++) {
+			const int par = call & 1;
+			const unsigned hb = cnt_smem_u32(hits + par * cells + cc);
+			float *pl = parts + (size_t)par * 2 * ACC_VW * 32;
+			if (call >= 2)          /* the updaters have consumed (and cleared) this parity's tile */
+				mbar_wait_parity(role_bar + 16 + 8 * par, (unsigned)((call >> 1) - 1) & 1u);
+#pragma unroll
+			for (int j = 0; j < VPW; j++) {
+				const int v = warp + FW * j;
+				float live = 0.0f, mx = -1000.0f;            /* display.cl:91,113 */
+				const int lo = v * Rv;
+#pragma unroll 1
+				for (int k = 0; k < nbv[j]; k++) {
+					const int s0 = lo + k * BOXR;
+					if (TMA) {
+						const float *wp = wsm + s0 + r;      /* weight of my row in step i: wp[RG * i] */
+						mbar_wait_parity(bar0 + 8u * slot, phase);
+						const float *bp = stage + (size_t)(warp * ACC_DEPTH + slot) * (BOXR * COLS) + lane;
+						constexpr int SUB = STEPS < 16 ? STEPS : 16;     /* steps whose loads are issued together */
+#pragma unroll
+						for (int i0 = 0; i0 < STEPS; i0 += SUB) {
+							float pw[SUB], wt[SUB];
+#pragma unroll
+							for (int i = 0; i < SUB; i++) {
+								pw[i] = bp[(i0 + i) * 32];
+								wt[i] = wp[RG * (i0 + i)];
+							}
+#pragma unroll
+							for (int i = 0; i < SUB; i++) {
+								live = fmaf(pw[i], wt[i], live);                  /* display.cl:149-150 */
+								mx = fmaxf(mx, pw[i]);                            /* :139 */
+								const unsigned off = bin_cell_offset<COLS>(pw[i], hofs, hscale2, kmax2);   /* :161-165 */
+								asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hb + off) : "memory");    /* :170-177 */
+							}
+						}
+						/* every lane has USED its values: the slot may be overwritten */
+						__syncwarp();
+						if (lane == 0)
+							issue();
+						if (++slot == ACC_DEPTH) {
+							slot = 0;
+							phase ^= 1u;
+						}
+					} else {
+						const float *wp = a.weights + s0 + r;
+						const unsigned ring = (unsigned)a.wf_pos + (unsigned)call * (unsigned)B;
+						float pw[STEPS];
+#pragma unroll
+						for (int i = 0; i < STEPS; i++) {
+							const int row = s0 + RG * i + r;
+							pw[i] = row < B ? __ldcg(wcol + (size_t)((ring + (unsigned)row) & mask) * N) : 0.0f;
+						}
+#pragma unroll
+						for (int i = 0; i < STEPS; i++) {
+							if (s0 + RG * i + r < B) {
+								live = fmaf(pw[i], __ldg(wp + RG * i), live);
+								mx = fmaxf(mx, pw[i]);
+								const unsigned off = bin_cell_offset<COLS>(pw[i], hofs, hscale2, kmax2);
+								asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hb + off) : "memory");
+							}
+						}
+					}
+				}
+				pl[v * 32 + lane] = live;
+				pl[ACC_VW * 32 + v * 32 + lane] = mx;
+			}
+			__syncwarp();           /* orders every lane's increments and partials before the arrive */
+			if (lane == 0)
+				mbar_arrive(role_bar + 8 * par);
+		}
+	} else {
+		/* ================= updater warps ================= */
+		const int ut = threadIdx.x - FW * 32;                /* 0 .. UW*32-1 */
+		const int uw = warp - FW;
+		const int r = lane / COLS, cc = lane % COLS;
+		(void)r;
+		const int half = N >> 1;
+		const int di = (col0 + cc) ^ half;                   /* display.cl:201 */
+		float y = 0.0f, m = 0.0f;
+		if (uw == 0 && lane < COLS) {
+			y = a.spectrum[di].y;
+			m = a.spectrum[N + di].y;
+		}
+		constexpr int UT = UW * 32;
+		float4 *h4 = reinterpret_cast<float4 *>(hist_s);
+		const float2 *lut = TMA ? lut_s : a.lut;
+
+		for (int call = 0; call < a.n_calls; call++) {
+			const int par = call & 1;
+			mbar_wait_parity(role_bar + 8 * par, (unsigned)(call >> 1) & 1u);
+			/* ---- rise / decay of the tile's cells, display.cl:217-254 ---- */
+			uint4 *hc4 = reinterpret_cast<uint4 *>(hits + par * cells);
+			constexpr int UNR = 4;
+			for (int g0 = ut; g0 < cells / 4; g0 += UT * UNR) {
+				uint4 hc[UNR];
+				float4 hv[UNR];
+#pragma unroll
+				for (int u = 0; u < UNR; u++) {
+					const int g = g0 + u * UT;
+					if (g < cells / 4) {
+						hc[u] = hc4[g];
+						hv[u] = h4[g];
+					} else {
+						hc[u] = make_uint4(0u, 0u, 0u, 0u);
+						hv[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < UNR; u++) {
+					const int g = g0 + u * UT;
+					const bool hit = (hc[u].x | hc[u].y | hc[u].z | hc[u].w) != 0u;
+					if (hit)
+						hc4[g] = make_uint4(0u, 0u, 0u, 0u);
+					if (hit || fmaxf(fmaxf(hv[u].x, hv[u].y), fmaxf(hv[u].z, hv[u].w)) > 0.01f) {
+						hv[u].x = rise_decay(hv[u].x, hc[u].x, lut);
+						hv[u].y = rise_decay(hv[u].y, hc[u].y, lut);
+						hv[u].z = rise_decay(hv[u].z, hc[u].z, lut);
+						hv[u].w = rise_decay(hv[u].w, hc[u].w, lut);
+						h4[g] = hv[u];
+					}
+				}
+			}
+			/* ---- live IIR and max hold, display.cl:186-214,257-310 ---- */
+			if (uw == 0) {
+				const float *pl = parts + (size_t)par * 2 * ACC_VW * 32;
+				float sum = 0.0f, bmax = -1000.0f;
+#pragma unroll
+				for (int w = 0; w < ACC_VW; w++) {
+					sum += pl[w * 32 + lane];
+					bmax = fmaxf(bmax, pl[ACC_VW * 32 + w * 32 + lane]);
+				}
+#pragma unroll
+				for (int o = COLS; o < 32; o <<= 1) {
+					sum += __shfl_xor_sync(0xffffffffu, sum, o);
+					bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+				}
+				if (!isfinite(y))
+					y = sum / (float)REF_ROWS;
+				y = __fadd_rn(__fmul_rn(y, a.live_carry), __fmul_rn(sum, a.alpha));
+				if (!isfinite(m))
+					m = -FLT_MAX;
+				m = __fadd_rn(__fmul_rn(m, a.mh_keep), __fmul_rn(a.mh_mix, y));
+				m = fmaxf(m, bmax);
+			}
+			__syncwarp();           /* all lanes done with this parity's tile and partials */
+			if (lane == 0)
+				mbar_arrive(role_bar + 16 + 8 * par);
+		}
+
+		/* tile state out: each updater thread stores the groups it owns */
+		{
+			constexpr int cpr = COLS / 4;
+			for (int g = ut; g < cells / 4; g += UT) {
+				const int bin = g / cpr, c4 = (g % cpr) * 4;
+				*reinterpret_cast<float4 *>(a.hist + (size_t)bin * N + col0 + c4) = h4[g];
+			}
+		}
+		if (uw == 0 && lane < COLS && a.n_calls > 0) {
+			const float xpos = ((float)di / (float)half) - 1.0f;     /* display.cl:209 */
+			a.spectrum[di] = make_float2(xpos, y);
+			a.spectrum[N + di] = make_float2(xpos, m);
+		}
+	}
+}
+
 /* first-use state, cl.c:406-465 */
 __global__ void fill_kernel(float *p, size_t n, float v)
 {

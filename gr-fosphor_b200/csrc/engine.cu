@@ -60,15 +60,15 @@ struct fosphor_cu {
 	cudaEvent_t cnt_done[2] = {nullptr, nullptr};
 	cudaEvent_t acc_done = nullptr;
 	cudaEvent_t cols_fork = nullptr, cols_join = nullptr;   /* column update runs beside the cell update */
-	int overlap = -1;                    /* env FOSPHOR_B200_OVERLAP: -1 (default) = automatic: on for the N = 512 /
-	                                      * 1024 persistent FFT kernel, off for the other plans (their FFT kernels fill
-	                                      * the SMs' shared memory, nothing can co-reside and halving the chunks only
-	                                      * costs); 1 = count/update of chunk c run on a second
-	                                      * stream while the FFT of chunk c+1 runs (needs a ring of >= 2 chunks).
-	                                      * The persistent FFT kernel then takes 2 CTAs per SM instead of 3 so
-	                                      * that count CTAs can co-reside: the FFT is HBM bound and barely
-	                                      * slower with 8 warps/SM (measured 67.8 vs 66.4 us), count is issue
-	                                      * bound - together +11 % on the bench step.  0 = one stream. */
+	int overlap = 0;                     /* env FOSPHOR_B200_OVERLAP: 1 = the accumulate kernels of chunk c run on a
+	                                      * second stream while the FFT of chunk c+1 runs (needs a ring of >= 2
+	                                      * chunks; the persistent FFT kernel then takes 2 CTAs per SM).  Default 0 =
+	                                      * one stream: measured with a 64-call ring, co-running buys nothing (old
+	                                      * split kernels 310 vs 306 Gsamples/s) or loses (fused kernel 283 vs 315):
+	                                      * both kernels slow down in proportion - the accumulate kernel re-reads the
+	                                      * waterfall chunk from HBM (134 MB per 32 calls, ncu) and competes for
+	                                      * the same issue slots - while halving the chunk doubles the launch
+	                                      * ramp/tail cost (~8 us per launch). */
 	bool two_streams_now = false;        /* set per process call */
 	int fft_ctas_per_sm = 0;             /* env FOSPHOR_B200_FFT_CTAS: force the CTAs/SM of the persistent FFT
 	                                      * kernel (0 = automatic: 3, or 2 when count runs beside it) */
@@ -76,6 +76,17 @@ struct fosphor_cu {
 	bool tmap_ok = false;
 	int count_variant = 1;               /* 1: TMA-staged count kernel where applicable, 0: plain
 	                                      * (env FOSPHOR_B200_COUNT_VARIANT) */
+	int acc_mode = -1;                   /* env FOSPHOR_B200_ACC: 1 = fused accumulate kernel (count + update in one
+	                                      * launch, state tile resident in shared memory), 0 = split count / update
+	                                      * kernels, -1 = by shape: fused when the batch is long against the bin
+	                                      * count (B >= 4K: counting dominates), split when the per-call state
+	                                      * update dominates (measured: cfg2 +5 %, cfg3 / N=512 sweep even or worse) */
+	int chunk_calls = 0;                 /* env FOSPHOR_B200_CHUNK_CALLS: cap on the calls folded per launch (0 = ring) */
+	int acc_cols = 8;                    /* columns per CTA of the fused kernel (env FOSPHOR_B200_ACC_COLS: 4 | 8) */
+	int acc_warps = 16;                  /* counter warps per CTA (env FOSPHOR_B200_ACC_WARPS: 8 | 16) */
+	int acc_box_max = 64;                /* largest TMA box in rows (env FOSPHOR_B200_ACC_BOX: 16 | 32 | 64) */
+	CUtensorMap acc_tmap[3];             /* waterfall ring, box = 16 / 32 / 64 rows x acc_cols columns */
+	bool acc_tmap_ok = false;
 
 	float *d_win = nullptr;
 	float2 *d_tw = nullptr;
@@ -396,10 +407,95 @@ void choose_slicing(const fosphor_cu *e, int n_calls, int batch, int *splits, in
 	*splits = (batch + rows - 1) / rows;
 }
 
+constexpr int ACC_UW = 4;        /* updater warps of the fused accumulate kernel */
+
+template <int COLS, int FW, int BOXR, bool TMA>
+cudaError_t fused_launch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st)
+{
+	using C = FusedCfg<COLS, FW, ACC_UW, BOXR>;
+	const size_t smem = C::smem(a.n_bins, a.batch, TMA);
+	static size_t configured = 0;          /* per kernel instantiation */
+	if (smem > configured) {
+		cudaError_t err = cudaFuncSetAttribute(accumulate_fused_kernel<COLS, FW, ACC_UW, BOXR, TMA>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (err != cudaSuccess)
+			return err;
+		configured = smem;
+	}
+	const CUtensorMap &tm = e->acc_tmap[BOXR == 64 ? 2 : (BOXR == 32 ? 1 : 0)];
+	accumulate_fused_kernel<COLS, FW, ACC_UW, BOXR, TMA><<<a.n / COLS, C::THREADS, smem, st>>>(a, tm);
+	return cudaGetLastError();
+}
+
+template <int COLS, int FW>
+cudaError_t fused_dispatch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st, int boxr)
+{
+	switch (boxr) {
+	case 64: return fused_launch<COLS, FW, 64, true>(e, a, st);
+	case 32: return fused_launch<COLS, FW, 32, true>(e, a, st);
+	case 16: return fused_launch<COLS, FW, 16, true>(e, a, st);
+	default: return fused_launch<COLS, FW, 16, false>(e, a, st);
+	}
+}
+
+/* one launch: count + rise/decay + live + max-hold of n_calls calls */
+int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cudaEvent_t count_done,
+                            int wf_pos, int n_calls, int batch)
+{
+	AccumArgs a;
+	memset(&a, 0, sizeof(a));
+	a.wf = e->d_wf;
+	a.hist = e->d_hist;
+	a.spectrum = e->d_spec;
+	a.weights = t->d_weights;
+	a.lut = t->d_lut;
+	a.n = e->p.fft_len;
+	a.n_bins = e->p.n_bins;
+	a.wf_mask = e->p.wf_rows - 1;
+	a.wf_pos = wf_pos;
+	a.batch = batch;
+	a.n_calls = n_calls;
+	a.hscale = e->histo_scale;
+	a.hofs = e->histo_ofs;
+	a.alpha = e->p.live_alpha;
+	a.live_carry = t->carry;
+	a.mh_keep = e->p.maxhold_keep;
+	a.mh_mix = e->p.maxhold_mix;
+	/* Largest TMA box (rows) that tiles every virtual warp's run of rows and never
+	 * straddles the ring end; 0 = plain loads.  Transport only: the row -> lane
+	 * assignment, hence every result bit, is the same for all of them. */
+	int boxr = 0;
+	if (e->acc_tmap_ok && batch <= ACC_WSM_MAX) {
+		const int rv = acc_rows_per_vwarp(batch);
+		for (int b = e->acc_box_max; b >= 16; b >>= 1)
+			if (batch % b == 0 && wf_pos % b == 0 && rv % b == 0 && (batch % rv) % b == 0 &&
+			    e->p.wf_rows % b == 0) {
+				boxr = b;
+				break;
+			}
+	}
+	prof_mark(e, 1, 0, st);
+	cudaError_t err;
+	if (e->acc_cols == 4)
+		err = e->acc_warps == 8 ? fused_dispatch<4, 8>(e, a, st, boxr) : fused_dispatch<4, 16>(e, a, st, boxr);
+	else
+		err = e->acc_warps == 8 ? fused_dispatch<8, 8>(e, a, st, boxr) : fused_dispatch<8, 16>(e, a, st, boxr);
+	prof_mark(e, 1, 1, st);
+	e->launches++;
+	CU_CHECK(e, err);
+	if (count_done)
+		CU_CHECK(e, cudaEventRecord(count_done, st));   /* the ring rows of this chunk are free again */
+	return 0;
+}
+
 /* fold n_calls calls (rows wf_pos .. wf_pos + n_calls*batch of the ring) into the state */
 int launch_accumulate(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cudaEvent_t count_done,
                       int wf_pos, int n_calls, int batch)
 {
+	/* path choice depends on (B, K) only, never on the ring position or the launch
+	 * folding: the two paths add the live spectrum in different orders */
+	if (e->acc_mode > 0 || (e->acc_mode < 0 && batch >= 4 * e->p.n_bins && (batch % 32) == 0 && e->acc_tmap_ok))
+		return launch_accumulate_fused(e, t, st, count_done, wf_pos, n_calls, batch);
 	AccumArgs a;
 	a.wf = e->d_wf;
 	a.hist = e->d_hist;
@@ -496,15 +592,15 @@ int process_device_calls(fosphor_cu *e, const float2 *in, int n_calls, int batch
 		 * chunk c+1 (main stream). */
 		const int ring_calls = e->p.wf_rows / batch;         /* >= 1: wf_rows >= batch_max */
 		int calls_per_chunk = ring_calls;
-		const bool auto_on = (e->p.fft_len == 1024 || e->p.fft_len == 512) && e->fft_variant != 0 &&
-		                     (hop & 1) == 0 && (reinterpret_cast<unsigned long long>(in) & 15ull) == 0;
-		const bool want = e->overlap > 0 || (e->overlap < 0 && auto_on);
+		const bool want = e->overlap > 0;
 		const bool two_streams = want && ring_calls >= 2 && n_calls > ring_calls / 2;
 		if (two_streams)
 			calls_per_chunk = ring_calls / 2;
 		e->two_streams_now = two_streams;
 		if (calls_per_chunk > e->max_slices)
 			calls_per_chunk = e->max_slices;
+		if (e->chunk_calls > 0 && calls_per_chunk > e->chunk_calls)
+			calls_per_chunk = e->chunk_calls;
 		cudaStream_t acc = two_streams ? e->acc_stream : e->stream;
 		int chunk = 0;
 		for (int c0 = 0; c0 < n_calls; c0 += calls_per_chunk, chunk++) {
@@ -784,6 +880,27 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 				gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
 				CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 			e->tmap_ok = (cr == CUDA_SUCCESS) && (w % TMA_ROWS) == 0;
+			if (const char *v = getenv("FOSPHOR_B200_ACC"))
+				e->acc_mode = atoi(v);
+			/* fused kernel: narrow tiles so that N / cols CTAs fill the chip */
+			e->acc_cols = (p.fft_len <= 512 || p.n_bins > 2048) ? 4 : 8;
+			if (const char *v = getenv("FOSPHOR_B200_ACC_COLS"))
+				e->acc_cols = atoi(v) == 4 ? 4 : 8;
+			if (const char *v = getenv("FOSPHOR_B200_CHUNK_CALLS"))
+				e->chunk_calls = atoi(v);
+			if (const char *v = getenv("FOSPHOR_B200_ACC_WARPS"))
+				e->acc_warps = atoi(v) == 8 ? 8 : 16;
+			if (const char *v = getenv("FOSPHOR_B200_ACC_BOX"))
+				e->acc_box_max = atoi(v) == 0 ? 0 : (atoi(v) == 16 ? 16 : (atoi(v) == 32 ? 32 : 64));   /* 0: plain loads */
+			e->acc_tmap_ok = true;
+			for (int i = 0; i < 3; i++) {
+				const cuuint32_t abox[2] = {(cuuint32_t)e->acc_cols, (cuuint32_t)(16 << i)};
+				cr = reinterpret_cast<encode_fn>(fn)(&e->acc_tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, e->d_wf,
+					gdim, gstride, abox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+					CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+				if (cr != CUDA_SUCCESS || w < (size_t)(16 << i))
+					e->acc_tmap_ok = false;
+			}
 		} else {
 			cudaGetLastError();
 		}

@@ -256,28 +256,41 @@ def test_fallback_paths_odd_batches_and_unaligned_hop(torch_cuda):
 
 
 def test_kernel_variants_are_bit_identical(torch_cuda, monkeypatch):
-    """TMA-prefetching FFT kernels (warp-level for N = 512/1024, CTA-level for
-    2048/4096/8192) vs plain, TMA-staged count kernel vs plain, two-stream overlap
-    vs one stream: same arithmetic, bit-identical waterfall / histogram / spectrum
-    (several calls folded per launch)."""
+    """Transport variants must not change a single bit: TMA-prefetching FFT kernels
+    (warp-level for N = 512/1024, CTA-level for 2048/4096/8192) vs plain; fused
+    accumulate kernel with 64/32/16-row TMA boxes vs plain loads, 8 vs 16 warps;
+    two-stream overlap vs one stream (several calls folded per launch).  The older
+    split count/update kernels sum the live spectrum in another order: histogram and
+    waterfall still bit-identical, live/max within the parity tolerance."""
     torch = torch_cuda
+    names = ("FFT_VARIANT", "OVERLAP", "ACC", "ACC_WARPS", "ACC_BOX", "COUNT_VARIANT")
+    variants = (("2", "1", "1", "8", "64", "1"),      # engine defaults
+                ("0", "0", "1", "16", "16", "1"),
+                ("1", "1", "1", "8", "32", "1"),
+                ("3", "0", "1", "16", "0", "1"),      # plain loads in the fused kernel
+                ("2", "1", "0", "8", "64", "1"),      # split kernels, TMA-staged count
+                ("0", "0", "0", "8", "64", "0"))      # split kernels, plain count
     for n in (1024, 512, 2048, 4096, 8192):
         calls, b = (5, 1024) if n <= 1024 else (3, 256)
         x = signals.noise_tones(n * b * calls, n_fft=n, seed=77)
         d = _to_dev(torch, x)
         outs = []
-        for fftv, cntv, ov in (("2", "1", "1"), ("0", "0", "0"), ("1", "0", "1"), ("3", "1", "0")):
-            monkeypatch.setenv("FOSPHOR_B200_FFT_VARIANT", fftv)
-            monkeypatch.setenv("FOSPHOR_B200_COUNT_VARIANT", cntv)
-            monkeypatch.setenv("FOSPHOR_B200_OVERLAP", ov)
+        for var in variants:
+            for k, v in zip(names, var):
+                monkeypatch.setenv("FOSPHOR_B200_" + k, v)
             e = _engine(fft_len=n, n_bins=256, wf_rows=4096)
             assert e.process_device_multi(d.data_ptr(), calls, b) == 0
             _, h = e.finish()
             outs.append({k: v.copy() for k, v in h.items()})
             e.close()
-        for o in outs[1:]:
-            for key in ("waterfall", "histogram", "spectrum"):
-                assert np.array_equal(outs[0][key], o[key]), (n, key)
+        for var, o in zip(variants[1:], outs[1:]):
+            for key in ("waterfall", "histogram"):
+                assert np.array_equal(outs[0][key], o[key]), (n, key, var)
+            if var[2] == "1":
+                assert np.array_equal(outs[0]["spectrum"], o["spectrum"]), (n, "spectrum", var)
+            else:
+                parity.check_spectrum(o["spectrum"], outs[0]["spectrum"], wf_ref=outs[0]["waterfall"][:calls * b])
+        assert np.array_equal(outs[-1]["spectrum"], outs[-2]["spectrum"]), n
 
 
 # ---------------------------------------------------------------------------

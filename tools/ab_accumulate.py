@@ -1,0 +1,50 @@
+#!/usr/bin/env python3
+"""A/B timing of the accumulate stage variants (env knobs of engine.cu) on one GPU,
+cfg2 shape unless told otherwise.  Prints one JSON line per variant."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+import perf_configs  # noqa: E402
+
+
+def main():
+    import torch
+    shapes = {"cfg2": ("cfg2", 1024, 256, 4, 1024, 64, 32768, False, {}),
+              "cfg3": ("cfg3", 4096, 512, 8, 256, 32, 8192, True, {"t0d": 20.0}),
+              "cfg4": ("cfg4", 16384, 1024, 1, 1024, 4, 4096, False, {}),
+              "cfg2r64": ("cfg2r64", 1024, 256, 4, 1024, 128, 65536, False, {}),
+              "n512": ("n512", 512, 256, 4, 1024, 128, 65536, True, {})}
+    which = sys.argv[1:] or ["cfg2"]
+    variants = [
+        {"ACC": "0"},
+        {"ACC": "1", "ACC_WARPS": "8", "ACC_BOX": "64"},
+        {"ACC": "1", "ACC_WARPS": "8", "ACC_BOX": "64", "FFT_CTAS": "3"},
+        {"ACC": "1", "ACC_WARPS": "16", "ACC_BOX": "64"},
+    ]
+    if "chunks" in which:
+        which.remove("chunks")
+        variants = [{"ACC": a, "CHUNK_CALLS": c} for a in ("0", "1") for c in ("0", "16", "8", "4")]
+    for w in which:
+        name, n, k, ov, b, calls, rows, ieo, kw = shapes[w]
+        for var in variants:
+            for key, v in var.items():
+                os.environ["FOSPHOR_B200_" + key] = v
+            for mode in ("0", "1"):
+                os.environ["FOSPHOR_B200_OVERLAP"] = mode
+                r = perf_configs.run_one(torch, name, n, k, ov, b, calls, rows, ieo, **kw)
+                print(json.dumps({"shape": w, "variant": var, "two_stream": mode == "1",
+                                  "Msps": round(r["Msamples_per_s"]), "ms_per_step": round(r["ms_per_step"], 4),
+                                  "fft_us": round(r["fft_us_per_launch"], 1),
+                                  "acc_us": round(r["count_us_per_launch"], 1),
+                                  "upd_us": round(r["update_us_per_launch"], 1)}), flush=True)
+            for key in var:
+                os.environ.pop("FOSPHOR_B200_" + key)
+
+
+if __name__ == "__main__":
+    main()
