@@ -64,6 +64,7 @@ struct AccumArgs {
 	float hscale, hofs;       /* cl.c:1087-1088 */
 	float alpha, live_carry;  /* live_carry = (1-alpha)^B, display.cl:210       */
 	float mh_keep, mh_mix;    /* display.cl:303 */
+	float rho_rg;             /* fused kernel: (1-alpha)^(rows per warp step) */
 };
 
 /* display.cl:161-165: bin = (int)round(histo_scale * (pwr + histo_ofs)), round
@@ -546,46 +547,10 @@ update_kernel(const AccumArgs a, int cell_blocks, int cap)
 /* ------------------------------------------------------------------------ */
 /* Fused accumulate kernel: count + rise/decay + live IIR + max-hold            */
 /* ------------------------------------------------------------------------ */
-/*
- * One CTA owns COLS adjacent frequency columns for the whole launch and walks
- * the calls of the chunk in order, so the per-cell recurrence along the call
- * axis (display.cl:241-247) never leaves the SM: the COLS x K histogram cells
- * of the tile live in shared memory from the first call to the last, the hit
- * counts of a call are built and consumed in shared memory, and the only
- * global traffic is the log-power rows (read once, through the TMA engine) and
- * one read + one write of the tile's state per LAUNCH.  (The split count /
- * update kernels above move a u16 count plane per slice through HBM and spend
- * their issue slots on that bookkeeping.)
- *
- * Warp roles.  FW "counter" warps turn rows into hit counts and live/max
- * partials; UW "updater" warps apply the rise/decay step and the live / max
- * recurrences of call c while the counters are already busy with call c+1.
- * Hit tile and partials are double buffered by call parity; the two roles
- * meet only through mbarriers (cnt_done[par]: counters -> updaters,
- * hits_free[par]: updaters -> counters), never through a block barrier, so no
- * counter warp ever waits for another counter warp.
- *
- * Geometry: a warp step is 32/COLS consecutive rows x COLS columns.  The rows
- * of a call are dealt to ACC_VW = 16 "virtual warps" in contiguous runs of
- * Rv = 16 * ceil(B/16 / 16) rows; counter warp w takes virtual warps w,
- * w+FW, ...  A run is fetched in boxes of BOXR rows x COLS columns by the TMA
- * engine (2-D tensor map), each counter warp running its own ring of
- * ACC_DEPTH boxes that keeps going across call boundaries.  hits[bin][col]
- * holds plain totals: the rows of one step meet in it through shared-memory
- * atomics (a bank conflict costs a wavefront in the LSU, not an issue slot,
- * and the kernel is issue bound).
- *
- * Live-spectrum sums: lane (r, col) adds the rows of its virtual warp in row
- * order, the 16 virtual-warp partials are added in order, the 32/COLS row
- * groups by an xor butterfly - a fixed order that depends on (B, COLS) only,
- * not on FW, BOXR, the load path or how calls are folded into launches.
- *
- * TMA = false: same arithmetic with plain loads (BOXR = 16, rows past the
- * batch masked), for batches / ring positions that do not align to a box.
- */
 constexpr int ACC_VW = 16;        /* virtual warps: the unit of the row -> lane assignment */
-constexpr int ACC_DEPTH = 3;      /* TMA boxes in flight per counter warp */
-constexpr int ACC_WSM_MAX = 4096; /* TMA path: live weights of the batch staged in shared memory */
+constexpr int ACC_STAGE_ROWS = 2048; /* rows of the tile staged ahead by the producer warp */
+constexpr int ACC_LW = 2;          /* loader warps (the TMA path uses one lane of the first) */
+constexpr int ACC_LUT_MAX = 4096; /* batches up to this keep the (d, e) table in shared memory */
 
 template <int COLS>
 __device__ __forceinline__ unsigned bin_cell_offset(float pwr, float hofs, float hscale2, int kmax2)
@@ -622,58 +587,105 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar)
 template <int COLS, int FW, int UW, int BOXR>
 struct FusedCfg {
 	static_assert(COLS == 4 || COLS == 8 || COLS == 16 || COLS == 32, "tile width");
-	static_assert(BOXR % 16 == 0 && BOXR <= 256, "box rows");
+	static_assert(BOXR == 16 || BOXR == 64 || BOXR == 256, "box rows");
 	static_assert(ACC_VW % FW == 0, "counter warps divide the virtual ones");
 	static constexpr int RG = 32 / COLS;                 /* rows per warp step */
-	static constexpr int STEPS = BOXR / RG;              /* steps per box */
 	static constexpr int VPW = ACC_VW / FW;              /* virtual warps per counter warp */
-	static constexpr int THREADS = (FW + UW) * 32;
+	static constexpr int THREADS = (FW + UW + ACC_LW) * 32;   /* counters, updaters, loader warps */
+	static constexpr int DEPTH = ACC_STAGE_ROWS / BOXR;  /* boxes in the stage ring (power of two) */
 	static constexpr size_t BOX_BYTES = sizeof(float) * BOXR * COLS;
-	static constexpr size_t STAGE_BYTES = BOX_BYTES * ACC_DEPTH * FW;
-	static constexpr size_t BAR_BYTES = 512;             /* FW * ACC_DEPTH TMA barriers + 4 role barriers */
-	static_assert(8 * (ACC_DEPTH * FW + 4) <= BAR_BYTES, "barrier area");
+	static constexpr size_t STAGE_BYTES = BOX_BYTES * DEPTH;
+	static constexpr size_t BAR_BYTES = 8 * (2 * DEPTH + 4) + 96;   /* full[], empty[], 4 role barriers; keeps 128 B alignment */
 	static constexpr size_t PART_BYTES = sizeof(float) * 2 * 2 * ACC_VW * 32;
 	static size_t smem(int K, int batch, bool tma)
 	{
-		return (tma ? STAGE_BYTES + sizeof(float) * (size_t)((batch + 3) & ~3) + sizeof(float2) * (size_t)(batch + 1) : 0) +
-		       BAR_BYTES + PART_BYTES + sizeof(float) * 3 * (size_t)K * COLS + 128;
+		size_t bar = (BAR_BYTES + 127) & ~(size_t)127;
+		return (tma ? STAGE_BYTES : 0) + bar + PART_BYTES + sizeof(float) * 3 * (size_t)K * COLS +
+		       (batch <= ACC_LUT_MAX ? sizeof(float2) * (size_t)(batch + 1) : 0) + 128;
 	}
 };
 
-template <int COLS, int FW, int UW, int BOXR, bool TMA>
-__global__ void __launch_bounds__((FW + UW) * 32, 1)
+/* Fused accumulate kernel.
+ *
+ * One CTA owns COLS adjacent frequency columns for the whole launch and walks
+ * the calls of the chunk in order, so the per-cell recurrence along the call
+ * axis (display.cl:241-247) never leaves the SM: the COLS x K histogram cells
+ * of the tile live in shared memory from the first call to the last, the hit
+ * counts of a call are built and consumed in shared memory, and the only
+ * global traffic is the log-power rows (read once, through the TMA engine) and
+ * one read + one write of the tile's state per LAUNCH.
+ *
+ * Warp roles (no block barrier after the prologue; everything meets through
+ * mbarriers):
+ *   producer (1 warp)  streams the tile's rows - contiguous in the ring across
+ *                      call boundaries - as BOXR x COLS tensor-map boxes into a
+ *                      ring of DEPTH slots (full[] / empty[] barriers);
+ *   counters (FW)      turn rows into hit counts (shared-memory atomics on
+ *                      hits[bin][col]) and live / max partials;
+ *   updaters (UW)      apply rise/decay and the live / max-hold recurrences of
+ *                      call c while the counters are already on call c+1 (hit
+ *                      tile and partials double buffered by call parity:
+ *                      cnt_done[par] counters -> updaters, hits_free[par] back).
+ *
+ * Row -> lane assignment: a warp step is RG = 32/COLS consecutive rows x COLS
+ * columns; the rows of a call are dealt to ACC_VW = 16 virtual warps in
+ * contiguous runs of Rv = 16 * ceil(B/16 / 16) rows; counter warp w takes
+ * virtual warps w, w+FW, ...  The live-spectrum sum of a lane is a Horner
+ * recurrence over its rows (acc = acc * (1-alpha)^RG + pwr) scaled by the
+ * table weight of its last row; the 16 virtual-warp partials are added in
+ * order, the row groups by an xor butterfly - a fixed order that depends on
+ * (B, COLS) only, not on FW, BOXR, SUBR, the load path or the launch folding.
+ *
+ * SUBR = rows handled by one unrolled body (loads of SUBR/RG steps issued
+ * together).  TMA = false: same arithmetic with plain loads (rows past the
+ * batch masked), for batches / ring positions that do not align to a box.
+ */
+template <int COLS, int FW, int UW, int BOXR, int SUBR, int LOAD>
+__global__ void __launch_bounds__((FW + UW + ACC_LW) * 32, 1)
 accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 {
 	using C = FusedCfg<COLS, FW, UW, BOXR>;
-	constexpr int RG = C::RG, STEPS = C::STEPS, VPW = C::VPW;
+	constexpr int RG = C::RG, VPW = C::VPW, DEPTH = C::DEPTH;
+	constexpr int SSTEPS = SUBR / RG;                    /* steps per unrolled body */
+	static_assert(SUBR == 16 || SUBR == 64, "sub-block rows");
+	/* LOAD: 0 plain loads by the counters; 1 TMA tensor-map boxes (one producer lane);
+	 *       2 cp.async 16-byte copies by the loader warps (16 x 32 B rows per instruction):
+	 *       the TMA engine needs ~2.4 cycles per 32-byte box row, which bounds mode 1 */
+	constexpr bool TMA = LOAD != 0;                      /* rows staged in shared memory */
 	extern __shared__ __align__(128) unsigned char fz_smem[];
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int col0 = blockIdx.x * COLS;
 	const int K = a.n_bins, N = a.n, B = a.batch;
 	const int cells = K * COLS;
+	const int Rv = acc_rows_per_vwarp(B);
 
 	/* carve shared memory */
 	unsigned char *sp = fz_smem;
 	float *stage = reinterpret_cast<float *>(sp);
 	if (TMA) sp += C::STAGE_BYTES;
 	unsigned long long *bars = reinterpret_cast<unsigned long long *>(sp);
-	sp += C::BAR_BYTES;
+	sp += (C::BAR_BYTES + 127) & ~(size_t)127;
 	float *parts = reinterpret_cast<float *>(sp);        /* [2 parity][2 live/max][ACC_VW][32] */
 	sp += C::PART_BYTES;
 	unsigned *hits = reinterpret_cast<unsigned *>(sp);   /* [2 parity][K][COLS] */
 	sp += sizeof(unsigned) * 2 * (size_t)cells;
 	float *hist_s = reinterpret_cast<float *>(sp);       /* [K][COLS] */
 	sp += sizeof(float) * (size_t)cells;
-	float *wsm = reinterpret_cast<float *>(sp);          /* [B] live weights (TMA path: B <= ACC_WSM_MAX) */
-	sp += sizeof(float) * (size_t)((B + 3) & ~3);
-	float2 *lut_s = reinterpret_cast<float2 *>(sp);      /* [B+1] (d, e) table (TMA path) */
+	float2 *lut_s = reinterpret_cast<float2 *>(sp);      /* [B+1] (d, e) table when B <= ACC_LUT_MAX */
 
-	const unsigned role_bar = cnt_smem_u32(bars + ACC_DEPTH * FW);   /* cnt_done[0,1], hits_free[0,1] */
+	const unsigned full0 = cnt_smem_u32(bars);                   /* full[DEPTH]  */
+	const unsigned empty0 = full0 + 8u * DEPTH;                  /* empty[DEPTH] */
+	const unsigned role_bar = empty0 + 8u * DEPTH;               /* cnt_done[0,1], hits_free[0,1] */
 
 	if (threadIdx.x == 0) {
-		for (int i = 0; i < ACC_DEPTH * FW; i++)
-			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cnt_smem_u32(bars + i)));
+		/* virtual warps that consume one box */
+		const int sharers = BOXR > Rv ? BOXR / Rv : 1;
+		if (TMA)
+			for (int i = 0; i < DEPTH; i++) {
+				asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8u * i), "r"(LOAD == 2 ? 32 : 1));
+				asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8u * i), "r"(sharers));
+			}
 		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar), "r"(FW));
 		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar + 8), "r"(FW));
 		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar + 16), "r"(UW));
@@ -681,7 +693,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
-	/* tile state in, hit tiles cleared, weights staged */
+	/* tile state in, hit tiles cleared, table staged */
 	{
 		constexpr int cpr = COLS / 4;                /* float4 groups per bin row */
 		float4 *h4 = reinterpret_cast<float4 *>(hist_s);
@@ -692,68 +704,32 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 			z4[g] = make_uint4(0u, 0u, 0u, 0u);
 			z4[g + cells / 4] = make_uint4(0u, 0u, 0u, 0u);
 		}
-		if (TMA) {
-			for (int i = threadIdx.x; i < B; i += C::THREADS)
-				wsm[i] = __ldg(&a.weights[i]);
+		if (B <= ACC_LUT_MAX)
 			for (int i = threadIdx.x; i <= B; i += C::THREADS)
 				lut_s[i] = __ldg(&a.lut[i]);
-		}
 	}
 	__syncthreads();
 
 	if (warp < FW) {
 		/* ================= counter warps ================= */
 		const int r = lane / COLS, cc = lane % COLS;
-		const int Rv = acc_rows_per_vwarp(B);
 		const unsigned mask = (unsigned)a.wf_mask;
-		const unsigned bar0 = cnt_smem_u32(bars + warp * ACC_DEPTH);
-		const unsigned stage0 = cnt_smem_u32(stage) + (unsigned)(warp * ACC_DEPTH * C::BOX_BYTES);
-
-		/* boxes of my j-th virtual warp in one call (TMA: all runs are whole boxes) */
-		int nbv[VPW];
-#pragma unroll
-		for (int j = 0; j < VPW; j++) {
-			const int lo = (warp + FW * j) * Rv;
-			nbv[j] = lo < B ? (min(B, lo + Rv) - lo + BOXR - 1) / BOXR : 0;
-		}
-		int per_call = 0;
-#pragma unroll
-		for (int j = 0; j < VPW; j++)
-			per_call += nbv[j];
-
-		/* issue side of my TMA ring (lane 0 only): next box to request = box iss_t of call iss_call */
-		static_assert(VPW <= 2, "issue() handles one or two runs per counter warp");
-		int iss_call = per_call > 0 ? 0 : a.n_calls, iss_t = 0;
-		unsigned iss_slot = 0;
-		auto issue = [&]() {
-			if (iss_call < a.n_calls) {
-				const bool second = VPW > 1 && iss_t >= nbv[0];
-				const int v = second ? warp + FW : warp;
-				const int k = second ? iss_t - nbv[0] : iss_t;
-				const unsigned row = ((unsigned)a.wf_pos + (unsigned)iss_call * (unsigned)B +
-				                      (unsigned)(v * Rv + k * BOXR)) & mask;
-				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-				             ::"r"(bar0 + 8u * iss_slot), "r"((unsigned)C::BOX_BYTES) : "memory");
-				tma_load_2d(stage0 + iss_slot * (unsigned)C::BOX_BYTES, &tmap, col0, (int)row, bar0 + 8u * iss_slot);
-				iss_slot = iss_slot + 1 == ACC_DEPTH ? 0 : iss_slot + 1;
-				if (++iss_t == per_call) {
-					iss_t = 0;
-					iss_call++;
-				}
-			}
-		};
-
-		if (TMA && lane == 0) {
-#pragma unroll 1
-			for (int d = 0; d < ACC_DEPTH; d++)
-				issue();
-		}
-
 		const int kmax2 = 2 * (K - 1);
 		const float hscale2 = 2.0f * a.hscale;
 		const float hofs = a.hofs;
+		const float rho = a.rho_rg;                          /* (1-alpha)^RG */
 		const float *wcol = a.wf + col0 + cc;
-		unsigned slot = 0, phase = 0u;
+		const int CH = TMA ? (Rv < BOXR ? Rv : BOXR) : SUBR; /* rows per chunk (TMA: one box or one run) */
+
+		/* my runs: rows [lo, lo + rows) of every call, and the table weight of my last row */
+		int lo[VPW], rows[VPW];
+		float wtail[VPW];
+#pragma unroll
+		for (int j = 0; j < VPW; j++) {
+			lo[j] = (warp + FW * j) * Rv;
+			rows[j] = max(0, min(B - lo[j], Rv));
+			wtail[j] = rows[j] > r ? __ldg(&a.weights[lo[j] + r + RG * ((rows[j] - 1 - r) / RG)]) : 0.0f;
+		}
 
 		for (int call = 0; call < a.n_calls; call++) {
 			const int par = call & 1;
@@ -764,53 +740,47 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 #pragma unroll
 			for (int j = 0; j < VPW; j++) {
 				const int v = warp + FW * j;
-				float live = 0.0f, mx = -1000.0f;            /* display.cl:91,113 */
-				const int lo = v * Rv;
+				float acc = 0.0f, mx = -1000.0f;             /* display.cl:91,113 */
 #pragma unroll 1
-				for (int k = 0; k < nbv[j]; k++) {
-					const int s0 = lo + k * BOXR;
+				for (int c0 = 0; c0 < rows[j]; c0 += CH) {
 					if (TMA) {
-						const float *wp = wsm + s0 + r;      /* weight of my row in step i: wp[RG * i] */
-						mbar_wait_parity(bar0 + 8u * slot, phase);
-						const float *bp = stage + (size_t)(warp * ACC_DEPTH + slot) * (BOXR * COLS) + lane;
-						constexpr int SUB = STEPS < 16 ? STEPS : 16;     /* steps whose loads are issued together */
+						/* rows of the launch are contiguous in the ring: box n holds rows n*BOXR .. */
+						const unsigned g = (unsigned)call * (unsigned)B + (unsigned)(lo[j] + c0);
+						const unsigned n = g / BOXR, slot = n % DEPTH;
+						mbar_wait_parity(full0 + 8u * slot, (n / DEPTH) & 1u);
+						const float *bp = stage + (size_t)slot * (BOXR * COLS) + (g % BOXR) * COLS + lane;
+#pragma unroll 1
+						for (int s0 = 0; s0 < CH; s0 += SUBR, bp += SUBR * COLS) {
+							float pw[SSTEPS];
 #pragma unroll
-						for (int i0 = 0; i0 < STEPS; i0 += SUB) {
-							float pw[SUB], wt[SUB];
+							for (int i = 0; i < SSTEPS; i++)
+								pw[i] = bp[i * 32];
 #pragma unroll
-							for (int i = 0; i < SUB; i++) {
-								pw[i] = bp[(i0 + i) * 32];
-								wt[i] = wp[RG * (i0 + i)];
-							}
-#pragma unroll
-							for (int i = 0; i < SUB; i++) {
-								live = fmaf(pw[i], wt[i], live);                  /* display.cl:149-150 */
+							for (int i = 0; i < SSTEPS; i++) {
+								acc = fmaf(acc, rho, pw[i]);                      /* display.cl:149-150 (Horner) */
 								mx = fmaxf(mx, pw[i]);                            /* :139 */
 								const unsigned off = bin_cell_offset<COLS>(pw[i], hofs, hscale2, kmax2);   /* :161-165 */
 								asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hb + off) : "memory");    /* :170-177 */
 							}
 						}
-						/* every lane has USED its values: the slot may be overwritten */
+						/* every lane has USED its values: hand the box back */
 						__syncwarp();
 						if (lane == 0)
-							issue();
-						if (++slot == ACC_DEPTH) {
-							slot = 0;
-							phase ^= 1u;
-						}
+							mbar_arrive(empty0 + 8u * slot);
 					} else {
-						const float *wp = a.weights + s0 + r;
 						const unsigned ring = (unsigned)a.wf_pos + (unsigned)call * (unsigned)B;
-						float pw[STEPS];
+						const int s0 = lo[j] + c0;
+						const int lim = lo[j] + rows[j];
+						float pw[SSTEPS];
 #pragma unroll
-						for (int i = 0; i < STEPS; i++) {
+						for (int i = 0; i < SSTEPS; i++) {
 							const int row = s0 + RG * i + r;
-							pw[i] = row < B ? __ldcg(wcol + (size_t)((ring + (unsigned)row) & mask) * N) : 0.0f;
+							pw[i] = row < lim ? __ldcg(wcol + (size_t)((ring + (unsigned)row) & mask) * N) : 0.0f;
 						}
 #pragma unroll
-						for (int i = 0; i < STEPS; i++) {
-							if (s0 + RG * i + r < B) {
-								live = fmaf(pw[i], __ldg(wp + RG * i), live);
+						for (int i = 0; i < SSTEPS; i++) {
+							if (s0 + RG * i + r < lim) {
+								acc = fmaf(acc, rho, pw[i]);
 								mx = fmaxf(mx, pw[i]);
 								const unsigned off = bin_cell_offset<COLS>(pw[i], hofs, hscale2, kmax2);
 								asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hb + off) : "memory");
@@ -818,19 +788,18 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 						}
 					}
 				}
-				pl[v * 32 + lane] = live;
+				pl[v * 32 + lane] = __fmul_rn(acc, wtail[j]);
 				pl[ACC_VW * 32 + v * 32 + lane] = mx;
 			}
 			__syncwarp();           /* orders every lane's increments and partials before the arrive */
 			if (lane == 0)
 				mbar_arrive(role_bar + 8 * par);
 		}
-	} else {
+	} else if (warp < FW + UW) {
 		/* ================= updater warps ================= */
 		const int ut = threadIdx.x - FW * 32;                /* 0 .. UW*32-1 */
 		const int uw = warp - FW;
-		const int r = lane / COLS, cc = lane % COLS;
-		(void)r;
+		const int cc = lane % COLS;
 		const int half = N >> 1;
 		const int di = (col0 + cc) ^ half;                   /* display.cl:201 */
 		float y = 0.0f, m = 0.0f;
@@ -840,7 +809,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 		}
 		constexpr int UT = UW * 32;
 		float4 *h4 = reinterpret_cast<float4 *>(hist_s);
-		const float2 *lut = TMA ? lut_s : a.lut;
+		const float2 *lut = B <= ACC_LUT_MAX ? lut_s : a.lut;
 
 		for (int call = 0; call < a.n_calls; call++) {
 			const int par = call & 1;
@@ -917,6 +886,51 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 			a.spectrum[di] = make_float2(xpos, y);
 			a.spectrum[N + di] = make_float2(xpos, m);
 		}
+	} else if constexpr (LOAD == 1) {
+		/* ================= producer (TMA) ================= */
+		if (warp == FW + UW && lane == 0) {
+			const unsigned mask = (unsigned)a.wf_mask;
+			const unsigned total = (unsigned)a.n_calls * (unsigned)(B / BOXR);
+			const unsigned stage0 = cnt_smem_u32(stage);
+			for (unsigned n = 0; n < total; n++) {
+				const unsigned slot = n % DEPTH;
+				if (n >= (unsigned)DEPTH)
+					mbar_wait_parity(empty0 + 8u * slot, ((n / DEPTH) - 1u) & 1u);
+				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+				             ::"r"(full0 + 8u * slot), "r"((unsigned)C::BOX_BYTES) : "memory");
+				tma_load_2d(stage0 + slot * (unsigned)C::BOX_BYTES, &tmap, col0,
+				            (int)(((unsigned)a.wf_pos + n * BOXR) & mask), full0 + 8u * slot);
+			}
+		}
+	} else if constexpr (LOAD == 2) {
+		/* ================= loaders (cp.async) ================= */
+		constexpr int LPR = COLS / 4;                        /* lanes (16 B each) per row */
+		constexpr int RPI = 32 / LPR < BOXR ? 32 / LPR : BOXR;   /* rows per warp instruction */
+		static_assert(BOXR % RPI == 0, "box is a whole number of copy instructions");
+		const bool copier = lane / LPR < RPI;                /* (4-column tiles, 16-row boxes: half the lanes) */
+		const int lw = warp - FW - UW;
+		const unsigned mask = (unsigned)a.wf_mask;
+		const unsigned total = (unsigned)a.n_calls * (unsigned)(B / BOXR);
+		const unsigned stage0 = cnt_smem_u32(stage) + (unsigned)((lane / LPR) * COLS * 4 + (lane % LPR) * 16);
+		const float *src0 = a.wf + col0 + (lane % LPR) * 4;
+		for (unsigned n = (unsigned)lw; n < total; n += ACC_LW) {
+			const unsigned slot = n % DEPTH;
+			if (n >= (unsigned)DEPTH)
+				mbar_wait_parity(empty0 + 8u * slot, ((n / DEPTH) - 1u) & 1u);
+			/* a box never straddles the ring end (ring position and size are multiples of BOXR) */
+			const unsigned row0 = (((unsigned)a.wf_pos + n * BOXR) & mask) + (unsigned)(lane / LPR);
+			const float *src = src0 + (size_t)row0 * N;
+			unsigned dst = stage0 + slot * (unsigned)C::BOX_BYTES;
+#pragma unroll 4
+			for (int i = 0; i < BOXR / RPI; i++) {
+				if (copier)
+					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+				src += (size_t)RPI * N;
+				dst += RPI * COLS * 4;
+			}
+			asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8u * slot) : "memory");
+		}
+		asm volatile("cp.async.wait_all;" ::: "memory");
 	}
 }
 

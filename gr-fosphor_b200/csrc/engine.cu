@@ -84,8 +84,10 @@ struct fosphor_cu {
 	int chunk_calls = 0;                 /* env FOSPHOR_B200_CHUNK_CALLS: cap on the calls folded per launch (0 = ring) */
 	int acc_cols = 8;                    /* columns per CTA of the fused kernel (env FOSPHOR_B200_ACC_COLS: 4 | 8) */
 	int acc_warps = 16;                  /* counter warps per CTA (env FOSPHOR_B200_ACC_WARPS: 8 | 16) */
-	int acc_box_max = 64;                /* largest TMA box in rows (env FOSPHOR_B200_ACC_BOX: 16 | 32 | 64) */
-	CUtensorMap acc_tmap[3];             /* waterfall ring, box = 16 / 32 / 64 rows x acc_cols columns */
+	int acc_box_max = 256;               /* largest TMA box in rows (env FOSPHOR_B200_ACC_BOX: 0 (plain loads) | 16 | 64 | 256) */
+	int acc_load = 2;                    /* staging path (env FOSPHOR_B200_ACC_LOAD): 2 = cp.async loader warps, 1 = TMA boxes */
+	int acc_sub_max = 64;                /* rows per unrolled body (env FOSPHOR_B200_ACC_SUB: 16 | 64) */
+	CUtensorMap acc_tmap[3];             /* waterfall ring, box = 16 / 64 / 256 rows x acc_cols columns */
 	bool acc_tmap_ok = false;
 
 	float *d_win = nullptr;
@@ -409,33 +411,38 @@ void choose_slicing(const fosphor_cu *e, int n_calls, int batch, int *splits, in
 
 constexpr int ACC_UW = 4;        /* updater warps of the fused accumulate kernel */
 
-template <int COLS, int FW, int BOXR, bool TMA>
+template <int COLS, int FW, int BOXR, int SUBR, int LOAD>
 cudaError_t fused_launch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st)
 {
 	using C = FusedCfg<COLS, FW, ACC_UW, BOXR>;
-	const size_t smem = C::smem(a.n_bins, a.batch, TMA);
+	const size_t smem = C::smem(a.n_bins, a.batch, LOAD != 0);
 	static size_t configured = 0;          /* per kernel instantiation */
 	if (smem > configured) {
-		cudaError_t err = cudaFuncSetAttribute(accumulate_fused_kernel<COLS, FW, ACC_UW, BOXR, TMA>,
+		cudaError_t err = cudaFuncSetAttribute(accumulate_fused_kernel<COLS, FW, ACC_UW, BOXR, SUBR, LOAD>,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (err != cudaSuccess)
 			return err;
 		configured = smem;
 	}
-	const CUtensorMap &tm = e->acc_tmap[BOXR == 64 ? 2 : (BOXR == 32 ? 1 : 0)];
-	accumulate_fused_kernel<COLS, FW, ACC_UW, BOXR, TMA><<<a.n / COLS, C::THREADS, smem, st>>>(a, tm);
+	const CUtensorMap &tm = e->acc_tmap[BOXR == 256 ? 2 : (BOXR == 64 ? 1 : 0)];
+	accumulate_fused_kernel<COLS, FW, ACC_UW, BOXR, SUBR, LOAD><<<a.n / COLS, C::THREADS, smem, st>>>(a, tm);
 	return cudaGetLastError();
 }
 
 template <int COLS, int FW>
-cudaError_t fused_dispatch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st, int boxr)
+cudaError_t fused_dispatch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st, int boxr, int subr, int load)
 {
-	switch (boxr) {
-	case 64: return fused_launch<COLS, FW, 64, true>(e, a, st);
-	case 32: return fused_launch<COLS, FW, 32, true>(e, a, st);
-	case 16: return fused_launch<COLS, FW, 16, true>(e, a, st);
-	default: return fused_launch<COLS, FW, 16, false>(e, a, st);
-	}
+	if (boxr == 256 && load == 2)
+		return subr == 64 ? fused_launch<COLS, FW, 256, 64, 2>(e, a, st) : fused_launch<COLS, FW, 256, 16, 2>(e, a, st);
+	if (boxr == 256)
+		return subr == 64 ? fused_launch<COLS, FW, 256, 64, 1>(e, a, st) : fused_launch<COLS, FW, 256, 16, 1>(e, a, st);
+	if (boxr == 64 && load == 2)
+		return subr == 64 ? fused_launch<COLS, FW, 64, 64, 2>(e, a, st) : fused_launch<COLS, FW, 64, 16, 2>(e, a, st);
+	if (boxr == 64)
+		return subr == 64 ? fused_launch<COLS, FW, 64, 64, 1>(e, a, st) : fused_launch<COLS, FW, 64, 16, 1>(e, a, st);
+	if (boxr == 16)
+		return load == 2 ? fused_launch<COLS, FW, 16, 16, 2>(e, a, st) : fused_launch<COLS, FW, 16, 16, 1>(e, a, st);
+	return fused_launch<COLS, FW, 16, 16, 0>(e, a, st);
 }
 
 /* one launch: count + rise/decay + live + max-hold of n_calls calls */
@@ -461,25 +468,27 @@ int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st
 	a.live_carry = t->carry;
 	a.mh_keep = e->p.maxhold_keep;
 	a.mh_mix = e->p.maxhold_mix;
-	/* Largest TMA box (rows) that tiles every virtual warp's run of rows and never
+	a.rho_rg = powf(1.0f - e->p.live_alpha, (float)(32 / e->acc_cols));
+	/* Largest TMA box (rows) that tiles the batch and the virtual warps' runs and never
 	 * straddles the ring end; 0 = plain loads.  Transport only: the row -> lane
 	 * assignment, hence every result bit, is the same for all of them. */
-	int boxr = 0;
-	if (e->acc_tmap_ok && batch <= ACC_WSM_MAX) {
+	int boxr = 0, subr = 16;
+	if (e->acc_tmap_ok) {
 		const int rv = acc_rows_per_vwarp(batch);
-		for (int b = e->acc_box_max; b >= 16; b >>= 1)
-			if (batch % b == 0 && wf_pos % b == 0 && rv % b == 0 && (batch % rv) % b == 0 &&
-			    e->p.wf_rows % b == 0) {
+		for (int b = e->acc_box_max; b >= 16; b >>= 2)
+			if (batch % b == 0 && wf_pos % b == 0 && e->p.wf_rows % b == 0 && (b % rv == 0 || rv % b == 0)) {
 				boxr = b;
+				const int ch = rv < b ? rv : b;
+				subr = (ch % 64 == 0 && e->acc_sub_max >= 64) ? 64 : 16;
 				break;
 			}
 	}
 	prof_mark(e, 1, 0, st);
 	cudaError_t err;
 	if (e->acc_cols == 4)
-		err = e->acc_warps == 8 ? fused_dispatch<4, 8>(e, a, st, boxr) : fused_dispatch<4, 16>(e, a, st, boxr);
+		err = e->acc_warps == 8 ? fused_dispatch<4, 8>(e, a, st, boxr, subr, e->acc_load) : fused_dispatch<4, 16>(e, a, st, boxr, subr, e->acc_load);
 	else
-		err = e->acc_warps == 8 ? fused_dispatch<8, 8>(e, a, st, boxr) : fused_dispatch<8, 16>(e, a, st, boxr);
+		err = e->acc_warps == 8 ? fused_dispatch<8, 8>(e, a, st, boxr, subr, e->acc_load) : fused_dispatch<8, 16>(e, a, st, boxr, subr, e->acc_load);
 	prof_mark(e, 1, 1, st);
 	e->launches++;
 	CU_CHECK(e, err);
@@ -890,15 +899,21 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 				e->chunk_calls = atoi(v);
 			if (const char *v = getenv("FOSPHOR_B200_ACC_WARPS"))
 				e->acc_warps = atoi(v) == 8 ? 8 : 16;
-			if (const char *v = getenv("FOSPHOR_B200_ACC_BOX"))
-				e->acc_box_max = atoi(v) == 0 ? 0 : (atoi(v) == 16 ? 16 : (atoi(v) == 32 ? 32 : 64));   /* 0: plain loads */
+			if (const char *v = getenv("FOSPHOR_B200_ACC_BOX")) {
+				const int b = atoi(v);
+				e->acc_box_max = b >= 256 ? 256 : (b >= 64 ? 64 : (b >= 16 ? 16 : 0));
+			}
+			if (const char *v = getenv("FOSPHOR_B200_ACC_LOAD"))
+				e->acc_load = atoi(v) == 1 ? 1 : 2;
+			if (const char *v = getenv("FOSPHOR_B200_ACC_SUB"))
+				e->acc_sub_max = atoi(v) >= 64 ? 64 : 16;
 			e->acc_tmap_ok = true;
 			for (int i = 0; i < 3; i++) {
-				const cuuint32_t abox[2] = {(cuuint32_t)e->acc_cols, (cuuint32_t)(16 << i)};
+				const cuuint32_t abox[2] = {(cuuint32_t)e->acc_cols, (cuuint32_t)(16 << (2 * i))};
 				cr = reinterpret_cast<encode_fn>(fn)(&e->acc_tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, e->d_wf,
 					gdim, gstride, abox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
 					CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-				if (cr != CUDA_SUCCESS || w < (size_t)(16 << i))
+				if (cr != CUDA_SUCCESS)
 					e->acc_tmap_ok = false;
 			}
 		} else {

@@ -22,9 +22,10 @@ def main():
     which = sys.argv[1:] or ["cfg2"]
     variants = [
         {"ACC": "0"},
-        {"ACC": "1", "ACC_WARPS": "8", "ACC_BOX": "64"},
-        {"ACC": "1", "ACC_WARPS": "8", "ACC_BOX": "64", "FFT_CTAS": "3"},
-        {"ACC": "1", "ACC_WARPS": "16", "ACC_BOX": "64"},
+        {"ACC": "1", "ACC_LOAD": "1"},
+        {"ACC": "1", "ACC_LOAD": "2"},
+        {"ACC": "1", "ACC_LOAD": "2", "ACC_BOX": "64"},
+        {"ACC": "1", "ACC_LOAD": "2", "ACC_WARPS": "8"},
     ]
     if "chunks" in which:
         which.remove("chunks")
@@ -34,7 +35,7 @@ def main():
         for var in variants:
             for key, v in var.items():
                 os.environ["FOSPHOR_B200_" + key] = v
-            for mode in ("0", "1"):
+            for mode in ("0",):
                 os.environ["FOSPHOR_B200_OVERLAP"] = mode
                 r = perf_configs.run_one(torch, name, n, k, ov, b, calls, rows, ieo, **kw)
                 print(json.dumps({"shape": w, "variant": var, "two_stream": mode == "1",
