@@ -549,7 +549,7 @@ update_kernel(const AccumArgs a, int cell_blocks, int cap)
 /* ------------------------------------------------------------------------ */
 constexpr int ACC_VW = 16;        /* virtual warps: the unit of the row -> lane assignment */
 constexpr int ACC_STAGE_ROWS = 2048; /* rows of the tile staged ahead by the producer warp */
-constexpr int ACC_LW = 2;          /* loader warps (the TMA path uses one lane of the first) */
+constexpr int ACC_XW = 2;          /* extra warps: one for the live / max-hold columns, one TMA producer */
 constexpr int ACC_LUT_MAX = 4096; /* batches up to this keep the (d, e) table in shared memory */
 
 template <int COLS>
@@ -591,7 +591,7 @@ struct FusedCfg {
 	static_assert(ACC_VW % FW == 0, "counter warps divide the virtual ones");
 	static constexpr int RG = 32 / COLS;                 /* rows per warp step */
 	static constexpr int VPW = ACC_VW / FW;              /* virtual warps per counter warp */
-	static constexpr int THREADS = (FW + UW + ACC_LW) * 32;   /* counters, updaters, loader warps */
+	static constexpr int THREADS = (FW + UW + ACC_XW) * 32;   /* counters, cell updaters, column warp, producer */
 	static constexpr int DEPTH = ACC_STAGE_ROWS / BOXR;  /* boxes in the stage ring (power of two) */
 	static constexpr size_t BOX_BYTES = sizeof(float) * BOXR * COLS;
 	static constexpr size_t STAGE_BYTES = BOX_BYTES * DEPTH;
@@ -622,10 +622,14 @@ struct FusedCfg {
  *                      ring of DEPTH slots (full[] / empty[] barriers);
  *   counters (FW)      turn rows into hit counts (shared-memory atomics on
  *                      hits[bin][col]) and live / max partials;
- *   updaters (UW)      apply rise/decay and the live / max-hold recurrences of
- *                      call c while the counters are already on call c+1 (hit
- *                      tile and partials double buffered by call parity:
- *                      cnt_done[par] counters -> updaters, hits_free[par] back).
+ *   updaters (UW + 1)  apply rise/decay (UW cell warps) and the live / max-hold
+ *                      recurrences (one column warp) of call c while the
+ *                      counters are already on call c+1 (hit tile and partials
+ *                      double buffered by call parity: cnt_done[par] counters ->
+ *                      updaters, hits_free[par] back).  The update of a call is
+ *                      a dependent chain that shares issue slots with the
+ *                      counters: it must stay shorter than a counter's share of
+ *                      the call, hence many short updater warps.
  *
  * Row -> lane assignment: a warp step is RG = 32/COLS consecutive rows x COLS
  * columns; the rows of a call are dealt to ACC_VW = 16 virtual warps in
@@ -641,16 +645,16 @@ struct FusedCfg {
  * batch masked), for batches / ring positions that do not align to a box.
  */
 template <int COLS, int FW, int UW, int BOXR, int SUBR, int LOAD>
-__global__ void __launch_bounds__((FW + UW + ACC_LW) * 32, 1)
+__global__ void __launch_bounds__((FW + UW + ACC_XW) * 32, 1)
 accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 {
 	using C = FusedCfg<COLS, FW, UW, BOXR>;
 	constexpr int RG = C::RG, VPW = C::VPW, DEPTH = C::DEPTH;
 	constexpr int SSTEPS = SUBR / RG;                    /* steps per unrolled body */
 	static_assert(SUBR == 16 || SUBR == 64, "sub-block rows");
-	/* LOAD: 0 plain loads by the counters; 1 TMA tensor-map boxes (one producer lane);
-	 *       2 cp.async 16-byte copies by the loader warps (16 x 32 B rows per instruction):
-	 *       the TMA engine needs ~2.4 cycles per 32-byte box row, which bounds mode 1 */
+	/* LOAD: 0 plain loads by the counters; 1 TMA tensor-map boxes (one producer lane).
+	 * (cp.async loader warps were tried instead of the TMA producer: 15 % slower.) */
+	static_assert(LOAD == 0 || LOAD == 1, "load path");
 	constexpr bool TMA = LOAD != 0;                      /* rows staged in shared memory */
 	extern __shared__ __align__(128) unsigned char fz_smem[];
 
@@ -683,13 +687,13 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 		const int sharers = BOXR > Rv ? BOXR / Rv : 1;
 		if (TMA)
 			for (int i = 0; i < DEPTH; i++) {
-				asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8u * i), "r"(LOAD == 2 ? 32 : 1));
+				asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8u * i), "r"(1));
 				asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8u * i), "r"(sharers));
 			}
 		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar), "r"(FW));
 		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar + 8), "r"(FW));
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar + 16), "r"(UW));
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar + 24), "r"(UW));
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar + 16), "r"(UW + 1));
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(role_bar + 24), "r"(UW + 1));
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
@@ -701,9 +705,9 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 		for (int g = threadIdx.x; g < cells / 4; g += C::THREADS) {
 			const int bin = g / cpr, c4 = (g % cpr) * 4;
 			h4[g] = *reinterpret_cast<const float4 *>(a.hist + (size_t)bin * N + col0 + c4);
-			z4[g] = make_uint4(0u, 0u, 0u, 0u);
-			z4[g + cells / 4] = make_uint4(0u, 0u, 0u, 0u);
 		}
+		for (int g = threadIdx.x; g < 2 * cells / 4; g += C::THREADS)
+			z4[g] = make_uint4(0u, 0u, 0u, 0u);
 		if (B <= ACC_LUT_MAX)
 			for (int i = threadIdx.x; i <= B; i += C::THREADS)
 				lut_s[i] = __ldg(&a.lut[i]);
@@ -733,6 +737,8 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 
 		for (int call = 0; call < a.n_calls; call++) {
 			const int par = call & 1;
+			/* the rows of one warp step can collide in a bank (~3 wavefronts per increment, ncu); private
+			 * replicas per row were tried (2 and 4): what they save here they cost twice in the update */
 			const unsigned hb = cnt_smem_u32(hits + par * cells + cc);
 			float *pl = parts + (size_t)par * 2 * ACC_VW * 32;
 			if (call >= 2)          /* the updaters have consumed (and cleared) this parity's tile */
@@ -796,17 +802,8 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 				mbar_arrive(role_bar + 8 * par);
 		}
 	} else if (warp < FW + UW) {
-		/* ================= updater warps ================= */
+		/* ================= cell updater warps ================= */
 		const int ut = threadIdx.x - FW * 32;                /* 0 .. UW*32-1 */
-		const int uw = warp - FW;
-		const int cc = lane % COLS;
-		const int half = N >> 1;
-		const int di = (col0 + cc) ^ half;                   /* display.cl:201 */
-		float y = 0.0f, m = 0.0f;
-		if (uw == 0 && lane < COLS) {
-			y = a.spectrum[di].y;
-			m = a.spectrum[N + di].y;
-		}
 		constexpr int UT = UW * 32;
 		float4 *h4 = reinterpret_cast<float4 *>(hist_s);
 		const float2 *lut = B <= ACC_LUT_MAX ? lut_s : a.lut;
@@ -816,7 +813,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 			mbar_wait_parity(role_bar + 8 * par, (unsigned)(call >> 1) & 1u);
 			/* ---- rise / decay of the tile's cells, display.cl:217-254 ---- */
 			uint4 *hc4 = reinterpret_cast<uint4 *>(hits + par * cells);
-			constexpr int UNR = 4;
+			constexpr int UNR = 2;
 			for (int g0 = ut; g0 < cells / 4; g0 += UT * UNR) {
 				uint4 hc[UNR];
 				float4 hv[UNR];
@@ -846,29 +843,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 					}
 				}
 			}
-			/* ---- live IIR and max hold, display.cl:186-214,257-310 ---- */
-			if (uw == 0) {
-				const float *pl = parts + (size_t)par * 2 * ACC_VW * 32;
-				float sum = 0.0f, bmax = -1000.0f;
-#pragma unroll
-				for (int w = 0; w < ACC_VW; w++) {
-					sum += pl[w * 32 + lane];
-					bmax = fmaxf(bmax, pl[ACC_VW * 32 + w * 32 + lane]);
-				}
-#pragma unroll
-				for (int o = COLS; o < 32; o <<= 1) {
-					sum += __shfl_xor_sync(0xffffffffu, sum, o);
-					bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
-				}
-				if (!isfinite(y))
-					y = sum / (float)REF_ROWS;
-				y = __fadd_rn(__fmul_rn(y, a.live_carry), __fmul_rn(sum, a.alpha));
-				if (!isfinite(m))
-					m = -FLT_MAX;
-				m = __fadd_rn(__fmul_rn(m, a.mh_keep), __fmul_rn(a.mh_mix, y));
-				m = fmaxf(m, bmax);
-			}
-			__syncwarp();           /* all lanes done with this parity's tile and partials */
+			__syncwarp();           /* all lanes done with this parity's tile */
 			if (lane == 0)
 				mbar_arrive(role_bar + 16 + 8 * par);
 		}
@@ -881,14 +856,56 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 				*reinterpret_cast<float4 *>(a.hist + (size_t)bin * N + col0 + c4) = h4[g];
 			}
 		}
-		if (uw == 0 && lane < COLS && a.n_calls > 0) {
+	} else if (warp == FW + UW) {
+		/* ================= column warp: live IIR and max hold, display.cl:186-214,257-310 ================= */
+		const int cc = lane % COLS;
+		const int half = N >> 1;
+		const int di = (col0 + cc) ^ half;                   /* display.cl:201 */
+		float y = 0.0f, m = 0.0f;
+		if (lane < COLS) {
+			y = a.spectrum[di].y;
+			m = a.spectrum[N + di].y;
+		}
+		for (int call = 0; call < a.n_calls; call++) {
+			const int par = call & 1;
+			mbar_wait_parity(role_bar + 8 * par, (unsigned)(call >> 1) & 1u);
+			const float *pl = parts + (size_t)par * 2 * ACC_VW * 32;
+			float pv[ACC_VW], pm[ACC_VW];
+#pragma unroll
+			for (int w = 0; w < ACC_VW; w++) {
+				pv[w] = pl[w * 32 + lane];
+				pm[w] = pl[ACC_VW * 32 + w * 32 + lane];
+			}
+			__syncwarp();           /* partials are in registers: hand the buffer back early */
+			if (lane == 0)
+				mbar_arrive(role_bar + 16 + 8 * par);
+			float sum = 0.0f, bmax = -1000.0f;
+#pragma unroll
+			for (int w = 0; w < ACC_VW; w++) {
+				sum += pv[w];
+				bmax = fmaxf(bmax, pm[w]);
+			}
+#pragma unroll
+			for (int o = COLS; o < 32; o <<= 1) {
+				sum += __shfl_xor_sync(0xffffffffu, sum, o);
+				bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+			}
+			if (!isfinite(y))
+				y = sum / (float)REF_ROWS;
+			y = __fadd_rn(__fmul_rn(y, a.live_carry), __fmul_rn(sum, a.alpha));
+			if (!isfinite(m))
+				m = -FLT_MAX;
+			m = __fadd_rn(__fmul_rn(m, a.mh_keep), __fmul_rn(a.mh_mix, y));
+			m = fmaxf(m, bmax);
+		}
+		if (lane < COLS && a.n_calls > 0) {
 			const float xpos = ((float)di / (float)half) - 1.0f;     /* display.cl:209 */
 			a.spectrum[di] = make_float2(xpos, y);
 			a.spectrum[N + di] = make_float2(xpos, m);
 		}
 	} else if constexpr (LOAD == 1) {
 		/* ================= producer (TMA) ================= */
-		if (warp == FW + UW && lane == 0) {
+		if (lane == 0) {
 			const unsigned mask = (unsigned)a.wf_mask;
 			const unsigned total = (unsigned)a.n_calls * (unsigned)(B / BOXR);
 			const unsigned stage0 = cnt_smem_u32(stage);
@@ -902,35 +919,6 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 				            (int)(((unsigned)a.wf_pos + n * BOXR) & mask), full0 + 8u * slot);
 			}
 		}
-	} else if constexpr (LOAD == 2) {
-		/* ================= loaders (cp.async) ================= */
-		constexpr int LPR = COLS / 4;                        /* lanes (16 B each) per row */
-		constexpr int RPI = 32 / LPR < BOXR ? 32 / LPR : BOXR;   /* rows per warp instruction */
-		static_assert(BOXR % RPI == 0, "box is a whole number of copy instructions");
-		const bool copier = lane / LPR < RPI;                /* (4-column tiles, 16-row boxes: half the lanes) */
-		const int lw = warp - FW - UW;
-		const unsigned mask = (unsigned)a.wf_mask;
-		const unsigned total = (unsigned)a.n_calls * (unsigned)(B / BOXR);
-		const unsigned stage0 = cnt_smem_u32(stage) + (unsigned)((lane / LPR) * COLS * 4 + (lane % LPR) * 16);
-		const float *src0 = a.wf + col0 + (lane % LPR) * 4;
-		for (unsigned n = (unsigned)lw; n < total; n += ACC_LW) {
-			const unsigned slot = n % DEPTH;
-			if (n >= (unsigned)DEPTH)
-				mbar_wait_parity(empty0 + 8u * slot, ((n / DEPTH) - 1u) & 1u);
-			/* a box never straddles the ring end (ring position and size are multiples of BOXR) */
-			const unsigned row0 = (((unsigned)a.wf_pos + n * BOXR) & mask) + (unsigned)(lane / LPR);
-			const float *src = src0 + (size_t)row0 * N;
-			unsigned dst = stage0 + slot * (unsigned)C::BOX_BYTES;
-#pragma unroll 4
-			for (int i = 0; i < BOXR / RPI; i++) {
-				if (copier)
-					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-				src += (size_t)RPI * N;
-				dst += RPI * COLS * 4;
-			}
-			asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8u * slot) : "memory");
-		}
-		asm volatile("cp.async.wait_all;" ::: "memory");
 	}
 }
 

@@ -78,14 +78,12 @@ struct fosphor_cu {
 	                                      * (env FOSPHOR_B200_COUNT_VARIANT) */
 	int acc_mode = -1;                   /* env FOSPHOR_B200_ACC: 1 = fused accumulate kernel (count + update in one
 	                                      * launch, state tile resident in shared memory), 0 = split count / update
-	                                      * kernels, -1 = by shape: fused when the batch is long against the bin
-	                                      * count (B >= 4K: counting dominates), split when the per-call state
-	                                      * update dominates (measured: cfg2 +5 %, cfg3 / N=512 sweep even or worse) */
+	                                      * kernels, -1 = by shape: fused when the batch is at least as long as the
+	                                      * bin count (measured: cfg2 +14 %, cfg4 +9 %, N=512 sweep +10 %), split
+	                                      * when the per-call state update dominates (cfg3: B = K/2, even) */
 	int chunk_calls = 0;                 /* env FOSPHOR_B200_CHUNK_CALLS: cap on the calls folded per launch (0 = ring) */
 	int acc_cols = 8;                    /* columns per CTA of the fused kernel (env FOSPHOR_B200_ACC_COLS: 4 | 8) */
-	int acc_warps = 16;                  /* counter warps per CTA (env FOSPHOR_B200_ACC_WARPS: 8 | 16) */
 	int acc_box_max = 256;               /* largest TMA box in rows (env FOSPHOR_B200_ACC_BOX: 0 (plain loads) | 16 | 64 | 256) */
-	int acc_load = 2;                    /* staging path (env FOSPHOR_B200_ACC_LOAD): 2 = cp.async loader warps, 1 = TMA boxes */
 	int acc_sub_max = 64;                /* rows per unrolled body (env FOSPHOR_B200_ACC_SUB: 16 | 64) */
 	CUtensorMap acc_tmap[3];             /* waterfall ring, box = 16 / 64 / 256 rows x acc_cols columns */
 	bool acc_tmap_ok = false;
@@ -409,7 +407,7 @@ void choose_slicing(const fosphor_cu *e, int n_calls, int batch, int *splits, in
 	*splits = (batch + rows - 1) / rows;
 }
 
-constexpr int ACC_UW = 4;        /* updater warps of the fused accumulate kernel */
+constexpr int ACC_UW = 8;         /* updater warps of the fused accumulate kernel */
 
 template <int COLS, int FW, int BOXR, int SUBR, int LOAD>
 cudaError_t fused_launch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st)
@@ -430,18 +428,14 @@ cudaError_t fused_launch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st)
 }
 
 template <int COLS, int FW>
-cudaError_t fused_dispatch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st, int boxr, int subr, int load)
+cudaError_t fused_dispatch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st, int boxr, int subr)
 {
-	if (boxr == 256 && load == 2)
-		return subr == 64 ? fused_launch<COLS, FW, 256, 64, 2>(e, a, st) : fused_launch<COLS, FW, 256, 16, 2>(e, a, st);
 	if (boxr == 256)
 		return subr == 64 ? fused_launch<COLS, FW, 256, 64, 1>(e, a, st) : fused_launch<COLS, FW, 256, 16, 1>(e, a, st);
-	if (boxr == 64 && load == 2)
-		return subr == 64 ? fused_launch<COLS, FW, 64, 64, 2>(e, a, st) : fused_launch<COLS, FW, 64, 16, 2>(e, a, st);
 	if (boxr == 64)
 		return subr == 64 ? fused_launch<COLS, FW, 64, 64, 1>(e, a, st) : fused_launch<COLS, FW, 64, 16, 1>(e, a, st);
 	if (boxr == 16)
-		return load == 2 ? fused_launch<COLS, FW, 16, 16, 2>(e, a, st) : fused_launch<COLS, FW, 16, 16, 1>(e, a, st);
+		return fused_launch<COLS, FW, 16, 16, 1>(e, a, st);
 	return fused_launch<COLS, FW, 16, 16, 0>(e, a, st);
 }
 
@@ -486,9 +480,9 @@ int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st
 	prof_mark(e, 1, 0, st);
 	cudaError_t err;
 	if (e->acc_cols == 4)
-		err = e->acc_warps == 8 ? fused_dispatch<4, 8>(e, a, st, boxr, subr, e->acc_load) : fused_dispatch<4, 16>(e, a, st, boxr, subr, e->acc_load);
+		err = fused_dispatch<4, 16>(e, a, st, boxr, subr);
 	else
-		err = e->acc_warps == 8 ? fused_dispatch<8, 8>(e, a, st, boxr, subr, e->acc_load) : fused_dispatch<8, 16>(e, a, st, boxr, subr, e->acc_load);
+		err = fused_dispatch<8, 16>(e, a, st, boxr, subr);
 	prof_mark(e, 1, 1, st);
 	e->launches++;
 	CU_CHECK(e, err);
@@ -503,7 +497,7 @@ int launch_accumulate(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cuda
 {
 	/* path choice depends on (B, K) only, never on the ring position or the launch
 	 * folding: the two paths add the live spectrum in different orders */
-	if (e->acc_mode > 0 || (e->acc_mode < 0 && batch >= 4 * e->p.n_bins && (batch % 32) == 0 && e->acc_tmap_ok))
+	if (e->acc_mode > 0 || (e->acc_mode < 0 && batch >= e->p.n_bins && (batch % 16) == 0 && e->acc_tmap_ok))
 		return launch_accumulate_fused(e, t, st, count_done, wf_pos, n_calls, batch);
 	AccumArgs a;
 	a.wf = e->d_wf;
@@ -897,14 +891,10 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 				e->acc_cols = atoi(v) == 4 ? 4 : 8;
 			if (const char *v = getenv("FOSPHOR_B200_CHUNK_CALLS"))
 				e->chunk_calls = atoi(v);
-			if (const char *v = getenv("FOSPHOR_B200_ACC_WARPS"))
-				e->acc_warps = atoi(v) == 8 ? 8 : 16;
 			if (const char *v = getenv("FOSPHOR_B200_ACC_BOX")) {
 				const int b = atoi(v);
 				e->acc_box_max = b >= 256 ? 256 : (b >= 64 ? 64 : (b >= 16 ? 16 : 0));
 			}
-			if (const char *v = getenv("FOSPHOR_B200_ACC_LOAD"))
-				e->acc_load = atoi(v) == 1 ? 1 : 2;
 			if (const char *v = getenv("FOSPHOR_B200_ACC_SUB"))
 				e->acc_sub_max = atoi(v) >= 64 ? 64 : 16;
 			e->acc_tmap_ok = true;

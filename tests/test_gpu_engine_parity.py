@@ -258,20 +258,19 @@ def test_fallback_paths_odd_batches_and_unaligned_hop(torch_cuda):
 def test_kernel_variants_are_bit_identical(torch_cuda, monkeypatch):
     """Transport variants must not change a single bit: TMA-prefetching FFT kernels
     (warp-level for N = 512/1024, CTA-level for 2048/4096/8192) vs plain; fused
-    accumulate kernel with 256/64/16-row TMA boxes vs plain loads, 8 vs 16 counter warps;
+    accumulate kernel with 256/64/16-row TMA boxes vs plain loads;
     two-stream overlap vs one stream (several calls folded per launch).  The older
     split count/update kernels sum the live spectrum in another order: histogram and
     waterfall still bit-identical, live/max within the parity tolerance."""
     torch = torch_cuda
-    names = ("FFT_VARIANT", "OVERLAP", "ACC", "ACC_WARPS", "ACC_BOX", "ACC_SUB", "ACC_LOAD", "COUNT_VARIANT")
-    variants = (("2", "0", "1", "16", "256", "64", "2", "1"),     # fused kernel, engine defaults (cp.async loaders)
-                ("0", "0", "1", "8", "16", "16", "2", "1"),
-                ("1", "1", "1", "8", "64", "64", "1", "1"),       # TMA boxes
-                ("2", "1", "1", "16", "256", "16", "1", "1"),
-                ("2", "0", "1", "8", "64", "16", "2", "1"),
-                ("3", "0", "1", "16", "0", "16", "2", "1"),       # plain loads in the fused kernel
-                ("2", "1", "0", "8", "64", "64", "2", "1"),       # split kernels, TMA-staged count
-                ("0", "0", "0", "8", "64", "64", "2", "0"))       # split kernels, plain count
+    names = ("FFT_VARIANT", "OVERLAP", "ACC", "ACC_BOX", "ACC_SUB", "COUNT_VARIANT")
+    variants = (("2", "0", "1", "256", "64", "1"),     # fused kernel, engine defaults
+                ("0", "0", "1", "16", "16", "1"),
+                ("1", "1", "1", "64", "64", "1"),
+                ("2", "1", "1", "256", "16", "1"),
+                ("3", "0", "1", "0", "16", "1"),       # plain loads in the fused kernel
+                ("2", "1", "0", "64", "64", "1"),      # split kernels, TMA-staged count
+                ("0", "0", "0", "64", "64", "0"))      # split kernels, plain count
     for n in (1024, 512, 2048, 4096, 8192):
         calls, b = (5, 1024) if n <= 1024 else (3, 256)
         x = signals.noise_tones(n * b * calls, n_fft=n, seed=77)

@@ -21,11 +21,7 @@ def main():
               "n512": ("n512", 512, 256, 4, 1024, 128, 65536, True, {})}
     which = sys.argv[1:] or ["cfg2"]
     variants = [
-        {"ACC": "0"},
-        {"ACC": "1", "ACC_LOAD": "1"},
-        {"ACC": "1", "ACC_LOAD": "2"},
-        {"ACC": "1", "ACC_LOAD": "2", "ACC_BOX": "64"},
-        {"ACC": "1", "ACC_LOAD": "2", "ACC_WARPS": "8"},
+        {"ACC": "1", "ACC_REP": "1"},
     ]
     if "chunks" in which:
         which.remove("chunks")
