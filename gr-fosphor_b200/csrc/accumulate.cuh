@@ -548,7 +548,8 @@ update_kernel(const AccumArgs a, int cell_blocks, int cap)
 /* Fused accumulate kernel: count + rise/decay + live IIR + max-hold            */
 /* ------------------------------------------------------------------------ */
 constexpr int ACC_VW = 16;        /* virtual warps: the unit of the row -> lane assignment */
-constexpr int ACC_STAGE_ROWS = 2048; /* rows of the tile staged ahead by the producer warp */
+constexpr int ACC_STAGE_ROWS = 2048; /* rows of the tile staged ahead by the producer warp (full-size CTA) */
+constexpr int ACC_STAGE_ROWS_SLIM = 1024; /* ... by the slim CTA that shares its SM with FFT CTAs */
 constexpr int ACC_XW = 2;          /* extra warps: one for the live / max-hold columns, one TMA producer */
 constexpr int ACC_LUT_MAX = 4096; /* batches up to this keep the (d, e) table in shared memory */
 
@@ -592,7 +593,10 @@ struct FusedCfg {
 	static constexpr int RG = 32 / COLS;                 /* rows per warp step */
 	static constexpr int VPW = ACC_VW / FW;              /* virtual warps per counter warp */
 	static constexpr int THREADS = (FW + UW + ACC_XW) * 32;   /* counters, cell updaters, column warp, producer */
-	static constexpr int DEPTH = ACC_STAGE_ROWS / BOXR;  /* boxes in the stage ring (power of two) */
+	static constexpr bool SLIM = FW < ACC_VW;            /* co-resident variant: <= 48 registers, half the stage */
+	static constexpr int STAGE_ROWS = SLIM ? ACC_STAGE_ROWS_SLIM : ACC_STAGE_ROWS;
+	static constexpr int MIN_CTAS = SLIM ? 2 : 1;        /* launch bound only: keeps the register count under 73 (it is 48) */
+	static constexpr int DEPTH = STAGE_ROWS / BOXR;      /* boxes in the stage ring (power of two) */
 	static constexpr size_t BOX_BYTES = sizeof(float) * BOXR * COLS;
 	static constexpr size_t STAGE_BYTES = BOX_BYTES * DEPTH;
 	static constexpr size_t BAR_BYTES = 8 * (2 * DEPTH + 4) + 96;   /* full[], empty[], 4 role barriers; keeps 128 B alignment */
@@ -645,7 +649,7 @@ struct FusedCfg {
  * batch masked), for batches / ring positions that do not align to a box.
  */
 template <int COLS, int FW, int UW, int BOXR, int SUBR, int LOAD>
-__global__ void __launch_bounds__((FW + UW + ACC_XW) * 32, 1)
+__global__ void __launch_bounds__((FW + UW + ACC_XW) * 32, (FusedCfg<COLS, FW, UW, BOXR>::MIN_CTAS))
 accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 {
 	using C = FusedCfg<COLS, FW, UW, BOXR>;

@@ -33,6 +33,7 @@ enum { ST_BOOTING = 0, ST_PENDING, ST_READY };   /* cl.c:95-99 */
 constexpr int N_TABLES = 8;      /* cached (weights, lut) sets, one per distinct batch size */
 constexpr int MAX_SLICES = 128;  /* (call, row-split) slices folded by one count/update launch pair */
 constexpr size_t CNT_BUDGET = (size_t)1 << 30;
+constexpr int N_CHUNK_EV = 64;   /* chunks in flight tracked by the two-stream schedule */
 constexpr size_t UPD_SMEM_MAX = 96 * 1024;   /* dynamic shared memory of update_kernel */   /* bytes of u16 hit-count slices kept on the device */
 
 struct BatchTables {
@@ -56,8 +57,8 @@ struct fosphor_cu {
 	cudaStream_t own_stream = nullptr;
 	cudaStream_t stream = nullptr;       /* FFT kernel, copies to the host, everything the caller orders against */
 	cudaStream_t acc_stream = nullptr;   /* count / update kernels: overlap the next chunk's FFT */
-	cudaEvent_t fft_done[2] = {nullptr, nullptr};   /* ping-pong per chunk */
-	cudaEvent_t cnt_done[2] = {nullptr, nullptr};
+	cudaEvent_t fft_done[N_CHUNK_EV] = {};   /* per chunk, round robin */
+	cudaEvent_t cnt_done[N_CHUNK_EV] = {};
 	cudaEvent_t acc_done = nullptr;
 	cudaEvent_t cols_fork = nullptr, cols_join = nullptr;   /* column update runs beside the cell update */
 	int overlap = 0;                     /* env FOSPHOR_B200_OVERLAP: 1 = the accumulate kernels of chunk c run on a
@@ -70,6 +71,9 @@ struct fosphor_cu {
 	                                      * the same issue slots - while halving the chunk doubles the launch
 	                                      * ramp/tail cost (~8 us per launch). */
 	bool two_streams_now = false;        /* set per process call */
+	int overlap_chunk = 16;              /* env FOSPHOR_B200_OVERLAP_CHUNK: calls per chunk of the two-stream schedule */
+	int acc_slim = 1;                    /* env FOSPHOR_B200_ACC_SLIM: two-stream mode uses the 14-warp fused kernel that
+	                                      * is co-resident with two FFT CTAs per SM */
 	int fft_ctas_per_sm = 0;             /* env FOSPHOR_B200_FFT_CTAS: force the CTAs/SM of the persistent FFT
 	                                      * kernel (0 = automatic: 3, or 2 when count runs beside it) */
 	CUtensorMap wf_tmap;                 /* waterfall ring as a 2-D tensor, box = 16 rows x 32 columns */
@@ -408,35 +412,37 @@ void choose_slicing(const fosphor_cu *e, int n_calls, int batch, int *splits, in
 }
 
 constexpr int ACC_UW = 8;         /* updater warps of the fused accumulate kernel */
+constexpr int ACC_FW_SLIM = 8;    /* counter / updater warps of the slim variant that runs beside the FFT kernel: */
+constexpr int ACC_UW_SLIM = 4;    /* 14 warps x 48 registers fit next to two FFT CTAs (2 x 4 warps x 168 registers)  */
 
-template <int COLS, int FW, int BOXR, int SUBR, int LOAD>
+template <int COLS, int FW, int UW, int BOXR, int SUBR, int LOAD>
 cudaError_t fused_launch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st)
 {
-	using C = FusedCfg<COLS, FW, ACC_UW, BOXR>;
+	using C = FusedCfg<COLS, FW, UW, BOXR>;
 	const size_t smem = C::smem(a.n_bins, a.batch, LOAD != 0);
 	static size_t configured = 0;          /* per kernel instantiation */
 	if (smem > configured) {
-		cudaError_t err = cudaFuncSetAttribute(accumulate_fused_kernel<COLS, FW, ACC_UW, BOXR, SUBR, LOAD>,
+		cudaError_t err = cudaFuncSetAttribute(accumulate_fused_kernel<COLS, FW, UW, BOXR, SUBR, LOAD>,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (err != cudaSuccess)
 			return err;
 		configured = smem;
 	}
 	const CUtensorMap &tm = e->acc_tmap[BOXR == 256 ? 2 : (BOXR == 64 ? 1 : 0)];
-	accumulate_fused_kernel<COLS, FW, ACC_UW, BOXR, SUBR, LOAD><<<a.n / COLS, C::THREADS, smem, st>>>(a, tm);
+	accumulate_fused_kernel<COLS, FW, UW, BOXR, SUBR, LOAD><<<a.n / COLS, C::THREADS, smem, st>>>(a, tm);
 	return cudaGetLastError();
 }
 
-template <int COLS, int FW>
+template <int COLS, int FW, int UW>
 cudaError_t fused_dispatch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st, int boxr, int subr)
 {
 	if (boxr == 256)
-		return subr == 64 ? fused_launch<COLS, FW, 256, 64, 1>(e, a, st) : fused_launch<COLS, FW, 256, 16, 1>(e, a, st);
+		return subr == 64 ? fused_launch<COLS, FW, UW, 256, 64, 1>(e, a, st) : fused_launch<COLS, FW, UW, 256, 16, 1>(e, a, st);
 	if (boxr == 64)
-		return subr == 64 ? fused_launch<COLS, FW, 64, 64, 1>(e, a, st) : fused_launch<COLS, FW, 64, 16, 1>(e, a, st);
+		return subr == 64 ? fused_launch<COLS, FW, UW, 64, 64, 1>(e, a, st) : fused_launch<COLS, FW, UW, 64, 16, 1>(e, a, st);
 	if (boxr == 16)
-		return fused_launch<COLS, FW, 16, 16, 1>(e, a, st);
-	return fused_launch<COLS, FW, 16, 16, 0>(e, a, st);
+		return fused_launch<COLS, FW, UW, 16, 16, 1>(e, a, st);
+	return fused_launch<COLS, FW, UW, 16, 16, 0>(e, a, st);
 }
 
 /* one launch: count + rise/decay + live + max-hold of n_calls calls */
@@ -479,10 +485,15 @@ int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st
 	}
 	prof_mark(e, 1, 0, st);
 	cudaError_t err;
+	const bool slim = e->two_streams_now && e->acc_slim;
+	if (slim)
+		subr = 16;      /* 46 registers (the 64-row body needs 56): 14 warps fit beside two FFT CTAs */
 	if (e->acc_cols == 4)
-		err = fused_dispatch<4, 16>(e, a, st, boxr, subr);
+		err = slim ? fused_dispatch<4, ACC_FW_SLIM, ACC_UW_SLIM>(e, a, st, boxr, subr)
+		           : fused_dispatch<4, 16, ACC_UW>(e, a, st, boxr, subr);
 	else
-		err = fused_dispatch<8, 16>(e, a, st, boxr, subr);
+		err = slim ? fused_dispatch<8, ACC_FW_SLIM, ACC_UW_SLIM>(e, a, st, boxr, subr)
+		           : fused_dispatch<8, 16, ACC_UW>(e, a, st, boxr, subr);
 	prof_mark(e, 1, 1, st);
 	e->launches++;
 	CU_CHECK(e, err);
@@ -596,21 +607,28 @@ int process_device_calls(fosphor_cu *e, const float2 *in, int n_calls, int batch
 		const int ring_calls = e->p.wf_rows / batch;         /* >= 1: wf_rows >= batch_max */
 		int calls_per_chunk = ring_calls;
 		const bool want = e->overlap > 0;
-		const bool two_streams = want && ring_calls >= 2 && n_calls > ring_calls / 2;
+		int ov_chunk = e->overlap_chunk < ring_calls / 2 ? e->overlap_chunk : ring_calls / 2;
+		if (ov_chunk < 1) ov_chunk = 1;
+		const bool two_streams = want && ring_calls >= 2 && n_calls >= 2 * ov_chunk;
 		if (two_streams)
-			calls_per_chunk = ring_calls / 2;
+			calls_per_chunk = ov_chunk;
 		e->two_streams_now = two_streams;
 		if (calls_per_chunk > e->max_slices)
 			calls_per_chunk = e->max_slices;
 		if (e->chunk_calls > 0 && calls_per_chunk > e->chunk_calls)
 			calls_per_chunk = e->chunk_calls;
 		cudaStream_t acc = two_streams ? e->acc_stream : e->stream;
+		/* The FFT of chunk c overwrites ring rows last read by the accumulate launch of a
+		 * chunk no younger than c - lag (every chunk has at most calls_per_chunk calls):
+		 * waiting for that one - the acc stream is in order - frees them. */
+		int lag = ring_calls / calls_per_chunk;
+		if (lag > N_CHUNK_EV) lag = N_CHUNK_EV;
 		int chunk = 0;
 		for (int c0 = 0; c0 < n_calls; c0 += calls_per_chunk, chunk++) {
 			const int nc = n_calls - c0 < calls_per_chunk ? n_calls - c0 : calls_per_chunk;
-			const int pp = chunk & 1;
-			if (two_streams && chunk >= 2)       /* rows about to be overwritten were read by count(chunk-2) */
-				CU_CHECK(e, cudaStreamWaitEvent(e->stream, e->cnt_done[pp], 0));
+			const int pp = chunk % N_CHUNK_EV;
+			if (two_streams && chunk >= lag)
+				CU_CHECK(e, cudaStreamWaitEvent(e->stream, e->cnt_done[(chunk - lag) % N_CHUNK_EV], 0));
 			CU_CHECK(e, launch_fft(e, in + (long long)c0 * batch * hop, hop, e->wf_pos, nc * batch));
 			if (two_streams) {
 				CU_CHECK(e, cudaEventRecord(e->fft_done[pp], e->stream));
@@ -726,7 +744,7 @@ void fosphor_cu_destroy(struct fosphor_cu *e)
 			for (cudaEvent_t ev : e->prof_ev[k][j])
 				cudaEventDestroy(ev);
 	if (e->acc_stream) { cudaStreamSynchronize(e->acc_stream); cudaStreamDestroy(e->acc_stream); }
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < N_CHUNK_EV; i++) {
 		if (e->fft_done[i]) cudaEventDestroy(e->fft_done[i]);
 		if (e->cnt_done[i]) cudaEventDestroy(e->cnt_done[i]);
 	}
@@ -787,7 +805,7 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 	CREATE_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
 	e->stream = e->own_stream;
 	CREATE_CHECK(cudaStreamCreateWithFlags(&e->acc_stream, cudaStreamNonBlocking));
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < N_CHUNK_EV; i++) {
 		CREATE_CHECK(cudaEventCreateWithFlags(&e->fft_done[i], cudaEventDisableTiming));
 		CREATE_CHECK(cudaEventCreateWithFlags(&e->cnt_done[i], cudaEventDisableTiming));
 	}
@@ -796,6 +814,10 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 	CREATE_CHECK(cudaEventCreateWithFlags(&e->cols_join, cudaEventDisableTiming));
 	if (const char *v = getenv("FOSPHOR_B200_OVERLAP"))
 		e->overlap = atoi(v);
+	if (const char *v = getenv("FOSPHOR_B200_OVERLAP_CHUNK"))
+		e->overlap_chunk = atoi(v) > 0 ? atoi(v) : 1;
+	if (const char *v = getenv("FOSPHOR_B200_ACC_SLIM"))
+		e->acc_slim = atoi(v);
 
 	const size_t n = p.fft_len, k = p.n_bins, w = p.wf_rows;
 	CREATE_CHECK(cudaMalloc(&e->d_win, sizeof(float) * n));

@@ -26,12 +26,18 @@ def main():
     if "chunks" in which:
         which.remove("chunks")
         variants = [{"ACC": a, "CHUNK_CALLS": c} for a in ("0", "1") for c in ("0", "16", "8", "4")]
+    modes = ("0",)
+    if "twostream" in which:
+        which.remove("twostream")
+        modes = ("1",)
+        variants = [{"ACC": "1", "OVERLAP_CHUNK": c, "ACC_SLIM": s} for s in ("1", "0") for c in ("4", "8", "16", "32")]
+        variants.append({"ACC": "1", "OVERLAP_CHUNK": "8", "ACC_SLIM": "1", "FFT_CTAS": "3"})
     for w in which:
         name, n, k, ov, b, calls, rows, ieo, kw = shapes[w]
         for var in variants:
             for key, v in var.items():
                 os.environ["FOSPHOR_B200_" + key] = v
-            for mode in ("0",):
+            for mode in modes:
                 os.environ["FOSPHOR_B200_OVERLAP"] = mode
                 r = perf_configs.run_one(torch, name, n, k, ov, b, calls, rows, ieo, **kw)
                 print(json.dumps({"shape": w, "variant": var, "two_stream": mode == "1",
