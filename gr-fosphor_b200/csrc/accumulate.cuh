@@ -593,7 +593,7 @@ struct FusedCfg {
 	static constexpr int RG = 32 / COLS;                 /* rows per warp step */
 	static constexpr int VPW = ACC_VW / FW;              /* virtual warps per counter warp */
 	static constexpr int THREADS = (FW + UW + ACC_XW) * 32;   /* counters, cell updaters, column warp, producer */
-	static constexpr bool SLIM = FW < ACC_VW;            /* co-resident variant: <= 48 registers, half the stage */
+	static constexpr bool SLIM = FW + UW < ACC_VW;           /* co-resident variant: <= 48 registers, half the stage */
 	static constexpr int STAGE_ROWS = SLIM ? ACC_STAGE_ROWS_SLIM : ACC_STAGE_ROWS;
 	static constexpr int MIN_CTAS = SLIM ? 2 : 1;        /* launch bound only: keeps the register count under 73 (it is 48) */
 	static constexpr int DEPTH = STAGE_ROWS / BOXR;      /* boxes in the stage ring (power of two) */
@@ -701,22 +701,24 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
-	/* tile state in, hit tiles cleared, table staged */
-	{
+	__syncthreads();                /* barriers are live: the producer may start filling the stage ring ... */
+	/* ... while the other warps bring the tile state in, clear the hit tiles and stage the table */
+	constexpr int WORKERS = C::THREADS - 32;     /* every warp but the producer (the last one) */
+	if (threadIdx.x < WORKERS) {
 		constexpr int cpr = COLS / 4;                /* float4 groups per bin row */
 		float4 *h4 = reinterpret_cast<float4 *>(hist_s);
 		uint4 *z4 = reinterpret_cast<uint4 *>(hits);
-		for (int g = threadIdx.x; g < cells / 4; g += C::THREADS) {
+		for (int g = threadIdx.x; g < cells / 4; g += WORKERS) {
 			const int bin = g / cpr, c4 = (g % cpr) * 4;
 			h4[g] = *reinterpret_cast<const float4 *>(a.hist + (size_t)bin * N + col0 + c4);
 		}
-		for (int g = threadIdx.x; g < 2 * cells / 4; g += C::THREADS)
+		for (int g = threadIdx.x; g < 2 * cells / 4; g += WORKERS)
 			z4[g] = make_uint4(0u, 0u, 0u, 0u);
 		if (B <= ACC_LUT_MAX)
-			for (int i = threadIdx.x; i <= B; i += C::THREADS)
+			for (int i = threadIdx.x; i <= B; i += WORKERS)
 				lut_s[i] = __ldg(&a.lut[i]);
+		asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");
 	}
-	__syncthreads();
 
 	if (warp < FW) {
 		/* ================= counter warps ================= */

@@ -74,6 +74,8 @@ struct fosphor_cu {
 	int overlap_chunk = 16;              /* env FOSPHOR_B200_OVERLAP_CHUNK: calls per chunk of the two-stream schedule */
 	int acc_slim = 1;                    /* env FOSPHOR_B200_ACC_SLIM: two-stream mode uses the 14-warp fused kernel that
 	                                      * is co-resident with two FFT CTAs per SM */
+	int fft_pf = -1;                     /* env FOSPHOR_B200_FFT_PF: L2 prefetch distance (spectra) of the plain FFT kernel;
+	                                      * -1 = the number of resident CTAs, 0 = off */
 	int fft_ctas_per_sm = 0;             /* env FOSPHOR_B200_FFT_CTAS: force the CTAs/SM of the persistent FFT
 	                                      * kernel (0 = automatic: 3, or 2 when count runs beside it) */
 	CUtensorMap wf_tmap;                 /* waterfall ring as a 2-D tensor, box = 16 rows x 32 columns */
@@ -86,6 +88,7 @@ struct fosphor_cu {
 	                                      * bin count (measured: cfg2 +14 %, cfg4 +9 %, N=512 sweep +10 %), split
 	                                      * when the per-call state update dominates (cfg3: B = K/2, even) */
 	int chunk_calls = 0;                 /* env FOSPHOR_B200_CHUNK_CALLS: cap on the calls folded per launch (0 = ring) */
+	int acc_roles = 0;                   /* env FOSPHOR_B200_ACC_ROLES: counter/updater warps 1 = 16/8, 2 = 8/16, 3 = 4/16; 0 = by shape */
 	int acc_cols = 8;                    /* columns per CTA of the fused kernel (env FOSPHOR_B200_ACC_COLS: 4 | 8) */
 	int acc_box_max = 256;               /* largest TMA box in rows (env FOSPHOR_B200_ACC_BOX: 0 (plain loads) | 16 | 64 | 256) */
 	int acc_sub_max = 64;                /* rows per unrolled body (env FOSPHOR_B200_ACC_SUB: 16 | 64) */
@@ -216,9 +219,24 @@ cudaError_t plan_launch(fosphor_cu *e, const float2 *in, long long hop, int wf_p
                         float2 *cplx_out, int n_spectra)
 {
 	const int grid = (n_spectra + P::SPB - 1) / P::SPB;
+	/* L2 prefetch distance of the one-spectrum-per-CTA plans: the CTAs resident at once */
+	int pf = 0;
+	const bool aligned = ((reinterpret_cast<unsigned long long>(in) & 15ull) == 0) && ((hop & 1) == 0);
+	if (P::SPB == 1 && aligned && e->fft_pf != 0) {
+		if (e->fft_pf > 0) {
+			pf = e->fft_pf;
+		} else {
+			static int per_sm = 0;         /* per plan instantiation */
+			if (per_sm == 0 &&
+			    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_power_kernel<P, CPLX>,
+			                                                  P::THREADS, P::SMEM) != cudaSuccess)
+				per_sm = 1;
+			pf = e->sm_count * (per_sm > 0 ? per_sm : 1);
+		}
+	}
 	prof_mark(e, 0, 0);
 	fft_power_kernel<P, CPLX><<<grid, P::THREADS, P::SMEM, e->stream>>>(
-		in, hop, e->d_win, e->d_tw, e->d_wf, wf_pos, e->p.wf_rows - 1, cplx_out, n_spectra);
+		in, hop, e->d_win, e->d_tw, e->d_wf, wf_pos, e->p.wf_rows - 1, cplx_out, n_spectra, pf);
 	prof_mark(e, 0, 1);
 	e->launches++;
 	return cudaGetLastError();
@@ -255,7 +273,8 @@ template <class P>
 cudaError_t stream_launch(fosphor_cu *e, const float2 *in, long long hop, int wf_pos, int n_spectra)
 {
 	using C = StreamCfg<P>;
-	int grid = (n_spectra + C::WARPS - 1) / C::WARPS;
+	const int units = (n_spectra + C::SPW - 1) / C::SPW;   /* a warp takes SPW spectra per iteration */
+	int grid = (units + C::WARPS - 1) / C::WARPS;
 	int per_sm = C::CTAS_PER_SM;
 	if (e->fft_ctas_per_sm > 0 && e->fft_ctas_per_sm < per_sm)
 		per_sm = e->fft_ctas_per_sm;
@@ -488,12 +507,22 @@ int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st
 	const bool slim = e->two_streams_now && e->acc_slim;
 	if (slim)
 		subr = 16;      /* 46 registers (the 64-row body needs 56): 14 warps fit beside two FFT CTAs */
+	/* warp roles: counters / cell updaters.  The update of a call is K*COLS cells, the count
+	 * B*COLS samples: with few rows per call (B < 2K) the cell updaters are the critical path
+	 * and get the larger share of the CTA. */
+	int roles = e->acc_roles;
+	if (roles == 0)
+		roles = 2 * a.n_bins > batch ? 2 : 1;
 	if (e->acc_cols == 4)
 		err = slim ? fused_dispatch<4, ACC_FW_SLIM, ACC_UW_SLIM>(e, a, st, boxr, subr)
-		           : fused_dispatch<4, 16, ACC_UW>(e, a, st, boxr, subr);
+		    : roles == 2 ? fused_dispatch<4, 8, 16>(e, a, st, boxr, subr)
+		    : roles == 3 ? fused_dispatch<4, 4, 16>(e, a, st, boxr, subr)
+		                 : fused_dispatch<4, 16, ACC_UW>(e, a, st, boxr, subr);
 	else
 		err = slim ? fused_dispatch<8, ACC_FW_SLIM, ACC_UW_SLIM>(e, a, st, boxr, subr)
-		           : fused_dispatch<8, 16, ACC_UW>(e, a, st, boxr, subr);
+		    : roles == 2 ? fused_dispatch<8, 8, 16>(e, a, st, boxr, subr)
+		    : roles == 3 ? fused_dispatch<8, 4, 16>(e, a, st, boxr, subr)
+		                 : fused_dispatch<8, 16, ACC_UW>(e, a, st, boxr, subr);
 	prof_mark(e, 1, 1, st);
 	e->launches++;
 	CU_CHECK(e, err);
@@ -818,6 +847,8 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 		e->overlap_chunk = atoi(v) > 0 ? atoi(v) : 1;
 	if (const char *v = getenv("FOSPHOR_B200_ACC_SLIM"))
 		e->acc_slim = atoi(v);
+	if (const char *v = getenv("FOSPHOR_B200_ACC_ROLES"))
+		e->acc_roles = atoi(v);
 
 	const size_t n = p.fft_len, k = p.n_bins, w = p.wf_rows;
 	CREATE_CHECK(cudaMalloc(&e->d_win, sizeof(float) * n));
@@ -874,6 +905,8 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 			e->fft_variant = atoi(v);
 		if (const char *v = getenv("FOSPHOR_B200_FFT_CTAS"))
 			e->fft_ctas_per_sm = atoi(v);
+		if (const char *v = getenv("FOSPHOR_B200_FFT_PF"))
+			e->fft_pf = atoi(v);
 	}
 	{
 		size_t upd = sizeof(float2) * (size_t)(p.batch_max + 1);

@@ -39,7 +39,13 @@ struct FftPlan {
 	static constexpr int T = NB1 < 32 ? 32 : NB1; /* threads per spectrum    */
 	static constexpr int SPB = T == 32 ? 4 : 1;   /* spectra per CTA         */
 	static constexpr int THREADS = T * SPB;
-	static constexpr int PADSHIFT = ilog2c(R0);
+	/* exchange-buffer padding: one float2 every 2^PADSHIFT.  log2(R0) keeps the stride-R0 stores of
+	 * pass 0 conflict free; at least 4 so that the pass-1 stores of the R0 = 8 plans (two runs of 8
+	 * float2, R0*R1 apart) land in different halves of the 32 banks (ncu: 46 % of the shared
+	 * wavefronts of N = 2048 / 8192 were conflict replays with a shift of 3) */
+	static constexpr int PADSHIFT = ilog2c(R0) < 4 ? 4 : ilog2c(R0);
+	/* launch bound of the plain kernel = the CTAs/SM that shared memory allows (8192: 3 CTAs at <= 80 registers) */
+	static constexpr int MIN_CTAS = N_ <= 1024 ? 4 : (N_ == 2048 ? 8 : (N_ == 4096 ? 4 : (N_ == 8192 ? 3 : 1)));
 	static constexpr int SM_ELEMS = N + (N >> PADSHIFT);
 	static constexpr size_t SMEM = sizeof(float2) * (size_t)SM_ELEMS * SPB;
 	/* twiddle table: pass 1 [R1][P1] with P1 = R0, then pass 2 [R1][P2], P2 = R0*R1 */
@@ -75,11 +81,11 @@ __device__ __forceinline__ void sync_spectrum()
  * CPLX = true:  stores X[k] as cf32 [n_spectra][N]; used only by the
  *               stage-wise parity test of the transform (tests/test_fft_parity.py). */
 template <class P, bool CPLX>
-__global__ void __launch_bounds__(P::THREADS)
+__global__ void __launch_bounds__(P::THREADS, P::MIN_CTAS)
 fft_power_kernel(const float2 *__restrict__ in, long long hop,
                  const float *__restrict__ win, const float2 *__restrict__ tw,
                  float *__restrict__ wf, int wf_pos, int wf_mask,
-                 float2 *__restrict__ cplx_out, int n_spectra)
+                 float2 *__restrict__ cplx_out, int n_spectra, int pf_dist)
 {
 	constexpr int N = P::N, R0 = P::R0, R1 = P::R1;
 	extern __shared__ float2 smem[];
@@ -92,6 +98,13 @@ fft_power_kernel(const float2 *__restrict__ in, long long hop,
 
 	float2 *buf = smem + (size_t)sub * P::SM_ELEMS;
 	const float2 *x = in + (long long)s * hop;
+	if constexpr (P::SPB == 1) {
+		/* pull the spectrum of the CTA that will follow this one on the SM into L2 (pf_dist =
+		 * resident CTAs; 0 = off / unaligned spectra): its pass-0 loads then hit L2 */
+		if (tid == 0 && pf_dist > 0 && s + pf_dist < n_spectra)
+			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+			             ::"l"(in + (long long)(s + pf_dist) * hop), "r"((unsigned)(sizeof(float2) * N)) : "memory");
+	}
 	float *row = CPLX ? nullptr : wf + (size_t)((wf_pos + s) & wf_mask) * N;
 	float2 *crow = CPLX ? cplx_out + (size_t)s * N : nullptr;
 
@@ -219,15 +232,18 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
 template <class P>
 struct StreamCfg {
 	static_assert(P::NPASS == 2 && P::T == 32, "one warp per spectrum plans only");
+	/* N = 512 has 16 last-pass butterflies: a warp takes TWO spectra at a time so that
+	 * no lane idles in the radix-32 pass (lanes 0-15 spectrum A, 16-31 spectrum B) */
+	static constexpr int SPW = P::NB1 < 32 ? 32 / P::NB1 : 1;   /* spectra per warp and iteration */
 	static constexpr int WARPS = 4;
 	static constexpr int THREADS = WARPS * 32;
 	static constexpr int CTAS_PER_SM = 3;
-	static constexpr int BUF_ELEMS = P::SM_ELEMS;                 /* >= N: holds inputs, then the exchange */
+	static constexpr int BUF_ELEMS = P::SM_ELEMS * SPW;           /* >= SPW * N: holds inputs, then the exchange */
 	static constexpr size_t BUF_BYTES_ALL = sizeof(float2) * (size_t)BUF_ELEMS * 2 * WARPS;
 	static constexpr size_t SMEM = BUF_BYTES_ALL + 8 * 2 * WARPS;
 	/* TWREG variant: + the window, shared by the CTA */
 	static constexpr size_t SMEM_TWREG = SMEM + sizeof(float) * P::N;
-	static constexpr unsigned IN_BYTES = sizeof(float2) * P::N;
+	static constexpr unsigned IN_BYTES = sizeof(float2) * P::N;   /* one spectrum */
 };
 
 /* TWREG = false: window slice in registers, pass-1 twiddles fetched (L1) per spectrum.
@@ -261,6 +277,8 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 	__syncwarp();
 
 	/* window: registers (slice of this lane: pass-0 element lane + t*NB0) or shared memory */
+	constexpr int SPW = C::SPW;
+	const int q1 = lane / P::NB1, i1 = lane % P::NB1;    /* pass 1: spectrum slot and butterfly of this lane */
 	float wreg[TWREG ? 1 : R0];
 	const float *swin = reinterpret_cast<const float *>(smem_raw + C::SMEM);
 	float2 twreg[TWREG ? R1 : 1];
@@ -269,10 +287,10 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 		for (int i = threadIdx.x; i < N; i += C::THREADS)
 			sw[i] = __ldg(&win[i]);
 		__syncthreads();
-		if (lane < P::NB1) {
+		if (q1 < SPW) {
 #pragma unroll
 			for (int t = 1; t < R1; t++)
-				twreg[t] = __ldg(&tw[t * R0 + (lane & (R0 - 1))]);
+				twreg[t] = __ldg(&tw[t * R0 + (i1 & (R0 - 1))]);
 		}
 	} else {
 		if (lane < P::NB0) {
@@ -282,67 +300,82 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 		}
 	}
 
-	int s = gw;
-	if (s < n_spectra && lane == 0) {
-		mbar_expect_tx(bar0, C::IN_BYTES);
-		bulk_g2s(buf0, in + (long long)s * hop, C::IN_BYTES, bar0);
-	}
+	/* unit u = spectra u*SPW .. u*SPW+SPW-1 (the last unit may be short) */
+	const int n_units = (n_spectra + SPW - 1) / SPW;
+	auto request = [&](int u, unsigned slot) {           /* lane 0 only */
+		const int s0 = u * SPW;
+		const int nv = n_spectra - s0 < SPW ? n_spectra - s0 : SPW;
+		mbar_expect_tx(bar0 + 8 * slot, C::IN_BYTES * (unsigned)nv);
+		for (int q = 0; q < nv; q++)
+			bulk_g2s(buf0 + slot * BUF_BYTES + (unsigned)q * (unsigned)(sizeof(float2) * P::SM_ELEMS),
+			         in + (long long)(s0 + q) * hop, C::IN_BYTES, bar0 + 8 * slot);
+	};
+
+	int u = gw;
+	if (u < n_units && lane == 0)
+		request(u, 0u);
 	unsigned phases = 0u;                /* bit b = parity to wait for on barrier b */
 
-	for (int it = 0; s < n_spectra; it++, s += G) {
+	for (int it = 0; u < n_units; it++, u += G) {
 		const int b = it & 1;
 		float2 *buf = bufs + (size_t)b * C::BUF_ELEMS;
 
-		/* prefetch the next spectrum into the other buffer (last touched by this
+		/* prefetch the next unit into the other buffer (last touched by this
 		 * warp's generic-proxy loads/stores one iteration ago) */
 		__syncwarp();
-		if (lane == 0 && s + G < n_spectra) {
+		if (lane == 0 && u + G < n_units) {
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-			const unsigned nb = (unsigned)(b ^ 1);
-			mbar_expect_tx(bar0 + 8 * nb, C::IN_BYTES);
-			bulk_g2s(buf0 + nb * BUF_BYTES, in + (long long)(s + G) * hop, C::IN_BYTES, bar0 + 8 * nb);
+			request(u + G, (unsigned)(b ^ 1));
 		}
 
 		while (!mbar_try_wait(bar0 + 8 * b, (phases >> b) & 1u)) { }
 		phases ^= 1u << b;
 
-		float *row = wf + (size_t)((wf_pos + s) & wf_mask) * N;
-
-		/* ---- pass 0 ---- */
-		float2 v0[R0];
-		if (lane < P::NB0) {
+		/* ---- pass 0, one spectrum slot after the other (a short last unit transforms stale
+		 * shared memory in its empty slot; nothing of it is stored) ---- */
 #pragma unroll
-			for (int t = 0; t < R0; t++) {
-				const float2 x = buf[lane + t * P::NB0];
-				const float w = TWREG ? swin[lane + t * P::NB0] : wreg[t];
-				v0[t] = make_float2(x.x * w, x.y * w);               /* fft.cl:416-417 */
+		for (int q = 0; q < SPW; q++) {
+			float2 *bq = buf + q * P::SM_ELEMS;
+			float2 v0[R0];
+			if (lane < P::NB0) {
+#pragma unroll
+				for (int t = 0; t < R0; t++) {
+					const float2 x = bq[lane + t * P::NB0];
+					const float w = TWREG ? swin[lane + t * P::NB0] : wreg[t];
+					v0[t] = make_float2(x.x * w, x.y * w);               /* fft.cl:416-417 */
+				}
 			}
-		}
-		__syncwarp();                   /* inputs consumed: buf becomes the exchange buffer */
-		if (lane < P::NB0) {
-			dif<R0>(v0);
-			static_for<0, R0>([&](auto tc) {
-				constexpr int t = decltype(tc)::value;
-				buf[pad_idx<P>(lane * R0 + t)] = v0[brev<R0>(t)];
-			});
+			__syncwarp();                   /* inputs consumed: the slot becomes the exchange buffer */
+			if (lane < P::NB0) {
+				dif<R0>(v0);
+				static_for<0, R0>([&](auto tc) {
+					constexpr int t = decltype(tc)::value;
+					bq[pad_idx<P>(lane * R0 + t)] = v0[brev<R0>(t)];
+				});
+			}
 		}
 		__syncwarp();
 
 		/* ---- pass 1 (P = R0), last ---- */
-		if (lane < P::NB1) {
-			const int k = lane & (R0 - 1);
+		if (q1 < SPW) {
+			const float2 *bq = buf + q1 * P::SM_ELEMS;
+			const int s = u * SPW + q1;
+			float *row = wf + (size_t)((wf_pos + s) & wf_mask) * N;
+			const int k = i1 & (R0 - 1);
 			float2 v[R1];
 #pragma unroll
 			for (int t = 0; t < R1; t++)
-				v[t] = buf[pad_idx<P>(lane + t * P::NB1)];
+				v[t] = bq[pad_idx<P>(i1 + t * P::NB1)];
 #pragma unroll
 			for (int t = 1; t < R1; t++)
 				v[t] = cmul(v[t], TWREG ? twreg[t] : __ldg(&tw[t * R0 + k]));
 			dif<R1>(v);
-			static_for<0, R1>([&](auto tc) {
-				constexpr int t = decltype(tc)::value;
-				row[lane + t * P::NB1] = log_power(v[brev<R1>(t)]);
-			});
+			if (s < n_spectra) {
+				static_for<0, R1>([&](auto tc) {
+					constexpr int t = decltype(tc)::value;
+					row[i1 + t * P::NB1] = log_power(v[brev<R1>(t)]);
+				});
+			}
 		}
 	}
 }

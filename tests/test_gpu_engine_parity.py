@@ -255,6 +255,25 @@ def test_fallback_paths_odd_batches_and_unaligned_hop(torch_cuda):
     eng.close()
 
 
+def test_n512_pairs_with_odd_spectrum_counts(torch_cuda):
+    """N = 512: a warp of the streaming FFT kernel transforms two spectra at a time; odd
+    call sizes leave the last pair half empty and shift the pairing of the next call."""
+    torch = torch_cuda
+    n = 512
+    sizes = (7, 33, 1, 128, 5)
+    stream = signals.noise_tones(n * sum(sizes), n_fft=n, seed=93)
+    calls, pos = [], 0
+    for b in sizes:
+        calls.append(stream[pos:pos + b * n])
+        pos += b * n
+    eng, host, orc = _run_both(torch, dict(fft_len=n, n_bins=128, batch_mult=1), calls)
+    rows = np.arange(sum(sizes))
+    parity.check_waterfall(host["waterfall"], orc.waterfall, rows=rows)
+    parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=sum(sizes) * n)
+    parity.check_spectrum(host["spectrum"], orc.spectrum, wf_ref=orc.waterfall[rows])
+    eng.close()
+
+
 def test_kernel_variants_are_bit_identical(torch_cuda, monkeypatch):
     """Transport variants must not change a single bit: TMA-prefetching FFT kernels
     (warp-level for N = 512/1024, CTA-level for 2048/4096/8192) vs plain; fused

@@ -16,13 +16,23 @@ def main():
     import torch
     shapes = {"cfg2": ("cfg2", 1024, 256, 4, 1024, 64, 32768, False, {}),
               "cfg3": ("cfg3", 4096, 512, 8, 256, 32, 8192, True, {"t0d": 20.0}),
-              "cfg4": ("cfg4", 16384, 1024, 1, 1024, 4, 4096, False, {}),
+              "cfg4": ("cfg4", 16384, 1024, 1, 1024, 32, 16384, False, {}),
+              "cfg4r4": ("cfg4r4", 16384, 1024, 1, 1024, 4, 4096, False, {}),
+              "n2048": ("n2048", 2048, 256, 4, 1024, 32, 16384, True, {}),
+              "n4096": ("n4096", 4096, 256, 4, 1024, 32, 16384, True, {}),
+              "n8192": ("n8192", 8192, 256, 4, 1024, 32, 16384, True, {}),
+              "n16384": ("n16384", 16384, 256, 4, 1024, 32, 16384, True, {}),
               "cfg2r64": ("cfg2r64", 1024, 256, 4, 1024, 128, 65536, False, {}),
               "n512": ("n512", 512, 256, 4, 1024, 128, 65536, True, {})}
     which = sys.argv[1:] or ["cfg2"]
     variants = [
         {"ACC": "1", "ACC_REP": "1"},
     ]
+    # var=KEY:VAL,KEY:VAL ... : explicit variants (FOSPHOR_B200_<KEY> = VAL), "var=" is the default build
+    explicit = [w for w in which if w.startswith("var=")]
+    if explicit:
+        which = [w for w in which if not w.startswith("var=")]
+        variants = [dict(kv.split(":") for kv in w[4:].split(",") if kv) for w in explicit]
     if "chunks" in which:
         which.remove("chunks")
         variants = [{"ACC": a, "CHUNK_CALLS": c} for a in ("0", "1") for c in ("0", "16", "8", "4")]

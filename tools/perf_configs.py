@@ -104,11 +104,11 @@ def main():
     # cfg3: N=4096, 512 bins, overlap 8, tau=0.95 -> t0d=20, B=256
     res.append(run(torch, "cfg3 persistence stress", 4096, 512, 8, 256, 32, 8192, True, t0d=20.0))
     # cfg4 shape on one GPU (one channel): N=16384, 1024 bins, B=1024
-    res.append(run(torch, "cfg4 one channel", 16384, 1024, 1, 1024, 4, 4096, False))
+    res.append(run(torch, "cfg4 one channel", 16384, 1024, 1, 1024, 32, 16384, False))
     # cfg5 sweep: K=256, overlap 4, B=1024
     for n in (512, 1024, 2048, 4096, 8192, 16384):
-        rows = max(1024, min(32768, (1 << 25) // n))
-        res.append(run(torch, "cfg5 sweep N=%d" % n, n, 256, 4, 1024, max(1, rows // 1024) * 2, rows, True))
+        rows = 32768 if n <= 1024 else 16384          # the ring folds 32 / 16 calls per launch
+        res.append(run(torch, "cfg5 sweep N=%d" % n, n, 256, 4, 1024, (rows // 1024) * 2, rows, True))
     for r in res:
         r["frac_of_hbm_peak"] = r["algorithmic_GBps"] / peak
     print(json.dumps({"hbm_peak_GBps": peak, "results": res}, indent=1))
