@@ -65,6 +65,7 @@ struct AccumArgs {
 	float alpha, live_carry;  /* live_carry = (1-alpha)^B, display.cl:210       */
 	float mh_keep, mh_mix;    /* display.cl:303 */
 	float rho_rg;             /* fused kernel: (1-alpha)^(rows per warp step) */
+	int depth_log2;           /* fused kernel: log2 of the boxes in the stage ring */
 };
 
 /* display.cl:161-165: bin = (int)round(histo_scale * (pwr + histo_ofs)), round
@@ -551,6 +552,7 @@ constexpr int ACC_VW = 16;        /* virtual warps: the unit of the row -> lane 
 constexpr int ACC_STAGE_ROWS = 2048; /* rows of the tile staged ahead by the producer warp (full-size CTA) */
 constexpr int ACC_STAGE_ROWS_SLIM = 1024; /* ... by the slim CTA that shares its SM with FFT CTAs */
 constexpr int ACC_XW = 2;          /* extra warps: one for the live / max-hold columns, one TMA producer */
+constexpr unsigned ACC_WAIT_HINT_NS = 20000u; /* mbarrier.try_wait suspend-time hint */
 constexpr int ACC_LUT_MAX = 4096; /* batches up to this keep the (d, e) table in shared memory */
 
 template <int COLS>
@@ -562,21 +564,27 @@ __device__ __forceinline__ unsigned bin_cell_offset(float pwr, float hofs, float
 	return ((unsigned)j & ~1u) * (COLS * 2);         /* (j >> 1) * COLS * 4 */
 }
 
-/* rows per virtual warp and call */
+/* rows per virtual warp and call: contiguous runs, at least 64 rows so that the per-run
+ * overhead (barrier probes, pointer set-up, partial stores) is paid once per 16+ warp steps;
+ * small batches therefore use fewer than ACC_VW virtual warps */
 __host__ __device__ inline int acc_rows_per_vwarp(int batch)
 {
 	const int units = (batch + 15) / 16;
-	return 16 * ((units + ACC_VW - 1) / ACC_VW);
+	const int rv = 16 * ((units + ACC_VW - 1) / ACC_VW);
+	return rv < 64 ? 64 : rv;
 }
 
 __device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned parity)
 {
+	/* suspend-time hint (ns): the warp sleeps in the barrier unit instead of re-issuing the probe.
+	 * ncu of cfg3 (B = 256) without it: one third of all executed instructions were probes of
+	 * counter warps waiting for the updaters, taken from the very warps they were waiting for. */
 	unsigned ok;
 	do {
 		asm volatile("{\n\t.reg .pred p;\n\t"
-		             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
 		             "selp.u32 %0, 1, 0, p;\n\t}"
-		             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+		             : "=r"(ok) : "r"(bar), "r"(parity), "r"(ACC_WAIT_HINT_NS) : "memory");
 	} while (!ok);
 }
 
@@ -585,8 +593,9 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar)
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int COLS, int FW, int UW, int BOXR>
+template <int COLS, int FW, int UW, int BOXR, int GC = 1>
 struct FusedCfg {
+	static_assert(GC == 1 || GC == 2 || GC == 4, "calls per synchronisation group");
 	static_assert(COLS == 4 || COLS == 8 || COLS == 16 || COLS == 32, "tile width");
 	static_assert(BOXR == 16 || BOXR == 64 || BOXR == 256, "box rows");
 	static_assert(ACC_VW % FW == 0, "counter warps divide the virtual ones");
@@ -594,18 +603,33 @@ struct FusedCfg {
 	static constexpr int VPW = ACC_VW / FW;              /* virtual warps per counter warp */
 	static constexpr int THREADS = (FW + UW + ACC_XW) * 32;   /* counters, cell updaters, column warp, producer */
 	static constexpr bool SLIM = FW + UW < ACC_VW;           /* co-resident variant: <= 48 registers, half the stage */
-	static constexpr int STAGE_ROWS = SLIM ? ACC_STAGE_ROWS_SLIM : ACC_STAGE_ROWS;
 	static constexpr int MIN_CTAS = SLIM ? 2 : 1;        /* launch bound only: keeps the register count under 73 (it is 48) */
-	static constexpr int DEPTH = STAGE_ROWS / BOXR;      /* boxes in the stage ring (power of two) */
 	static constexpr size_t BOX_BYTES = sizeof(float) * BOXR * COLS;
-	static constexpr size_t STAGE_BYTES = BOX_BYTES * DEPTH;
-	static constexpr size_t BAR_BYTES = 8 * (2 * DEPTH + 4) + 96;   /* full[], empty[], 4 role barriers; keeps 128 B alignment */
-	static constexpr size_t PART_BYTES = sizeof(float) * 2 * 2 * ACC_VW * 32;
-	static size_t smem(int K, int batch, bool tma)
+	static constexpr int DEPTH_MAX = 8192 / BOXR;        /* boxes in the stage ring: a power of two chosen per launch */
+	static constexpr size_t BAR_BYTES = 8 * (2 * DEPTH_MAX + 4) + 96;   /* full[], empty[], 4 role barriers; keeps 128 B alignment */
+	static constexpr size_t PART_BYTES = sizeof(float) * 2 * GC * 2 * ACC_VW * 32;
+	/* everything but the stage ring */
+	static size_t smem_fixed(int K, int batch)
 	{
 		size_t bar = (BAR_BYTES + 127) & ~(size_t)127;
-		return (tma ? STAGE_BYTES : 0) + bar + PART_BYTES + sizeof(float) * 3 * (size_t)K * COLS +
+		return bar + PART_BYTES + sizeof(float) * (2 * GC + 1) * (size_t)K * COLS +
 		       (batch <= ACC_LUT_MAX ? sizeof(float2) * (size_t)(batch + 1) : 0) + 128;
+	}
+	/* The stage ring is what keeps HBM busy: one CTA per SM, so bytes in flight per SM = the ring
+	 * (64 KB gave 3.7 TB/s at cfg2: 2.6 us of latency per 32-byte row segment box).  Take what the
+	 * SM has left, up to DEPTH_MAX boxes; the slim variant shares its SM and stays at 1024 rows. */
+	static int depth_log2(int K, int batch, size_t smem_limit)
+	{
+		const size_t fixed = smem_fixed(K, batch);
+		int d = 0;
+		const int cap = SLIM ? (1024 / BOXR > 1 ? 1024 / BOXR : 1) : DEPTH_MAX;
+		while ((2 << d) <= cap && fixed + BOX_BYTES * (size_t)(2 << d) <= smem_limit)
+			d++;
+		return d;
+	}
+	static size_t smem(int K, int batch, bool tma, int dlog)
+	{
+		return (tma ? BOX_BYTES << dlog : 0) + smem_fixed(K, batch);
 	}
 };
 
@@ -648,12 +672,13 @@ struct FusedCfg {
  * together).  TMA = false: same arithmetic with plain loads (rows past the
  * batch masked), for batches / ring positions that do not align to a box.
  */
-template <int COLS, int FW, int UW, int BOXR, int SUBR, int LOAD>
-__global__ void __launch_bounds__((FW + UW + ACC_XW) * 32, (FusedCfg<COLS, FW, UW, BOXR>::MIN_CTAS))
+template <int COLS, int FW, int UW, int BOXR, int SUBR, int LOAD, int GC = 1>
+__global__ void __launch_bounds__((FW + UW + ACC_XW) * 32, (FusedCfg<COLS, FW, UW, BOXR, GC>::MIN_CTAS))
 accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap tmap)
 {
-	using C = FusedCfg<COLS, FW, UW, BOXR>;
-	constexpr int RG = C::RG, VPW = C::VPW, DEPTH = C::DEPTH;
+	using C = FusedCfg<COLS, FW, UW, BOXR, GC>;
+	constexpr int RG = C::RG;
+	const unsigned dlog = (unsigned)a.depth_log2, DEPTH = 1u << dlog;   /* boxes in the stage ring */
 	constexpr int SSTEPS = SUBR / RG;                    /* steps per unrolled body */
 	static_assert(SUBR == 16 || SUBR == 64, "sub-block rows");
 	/* LOAD: 0 plain loads by the counters; 1 TMA tensor-map boxes (one producer lane).
@@ -671,13 +696,13 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 	/* carve shared memory */
 	unsigned char *sp = fz_smem;
 	float *stage = reinterpret_cast<float *>(sp);
-	if (TMA) sp += C::STAGE_BYTES;
+	if (TMA) sp += C::BOX_BYTES << dlog;
 	unsigned long long *bars = reinterpret_cast<unsigned long long *>(sp);
 	sp += (C::BAR_BYTES + 127) & ~(size_t)127;
-	float *parts = reinterpret_cast<float *>(sp);        /* [2 parity][2 live/max][ACC_VW][32] */
+	float *parts = reinterpret_cast<float *>(sp);        /* [2 parity][GC calls][2 live/max][ACC_VW][32] */
 	sp += C::PART_BYTES;
-	unsigned *hits = reinterpret_cast<unsigned *>(sp);   /* [2 parity][K][COLS] */
-	sp += sizeof(unsigned) * 2 * (size_t)cells;
+	unsigned *hits = reinterpret_cast<unsigned *>(sp);   /* [2 parity][GC calls][K][COLS] */
+	sp += sizeof(unsigned) * 2 * GC * (size_t)cells;
 	float *hist_s = reinterpret_cast<float *>(sp);       /* [K][COLS] */
 	sp += sizeof(float) * (size_t)cells;
 	float2 *lut_s = reinterpret_cast<float2 *>(sp);      /* [B+1] (d, e) table when B <= ACC_LUT_MAX */
@@ -690,7 +715,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 		/* virtual warps that consume one box */
 		const int sharers = BOXR > Rv ? BOXR / Rv : 1;
 		if (TMA)
-			for (int i = 0; i < DEPTH; i++) {
+			for (unsigned i = 0; i < DEPTH; i++) {
 				asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8u * i), "r"(1));
 				asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8u * i), "r"(sharers));
 			}
@@ -712,11 +737,14 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 			const int bin = g / cpr, c4 = (g % cpr) * 4;
 			h4[g] = *reinterpret_cast<const float4 *>(a.hist + (size_t)bin * N + col0 + c4);
 		}
-		for (int g = threadIdx.x; g < 2 * cells / 4; g += WORKERS)
+		for (int g = threadIdx.x; g < 2 * GC * cells / 4; g += WORKERS)
 			z4[g] = make_uint4(0u, 0u, 0u, 0u);
 		if (B <= ACC_LUT_MAX)
 			for (int i = threadIdx.x; i <= B; i += WORKERS)
 				lut_s[i] = __ldg(&a.lut[i]);
+		/* partials of virtual warps that small batches never visit: 0 / -1000 (display.cl:91,113) */
+		for (int i = threadIdx.x; i < 2 * GC * 2 * ACC_VW * 32; i += WORKERS)
+			parts[i] = ((i / (ACC_VW * 32)) & 1) ? -1000.0f : 0.0f;
 		asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");
 	}
 
@@ -731,35 +759,47 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 		const float *wcol = a.wf + col0 + cc;
 		const int CH = TMA ? (Rv < BOXR ? Rv : BOXR) : SUBR; /* rows per chunk (TMA: one box or one run) */
 
-		/* my runs: rows [lo, lo + rows) of every call, and the table weight of my last row */
-		int lo[VPW], rows[VPW];
-		float wtail[VPW];
-#pragma unroll
-		for (int j = 0; j < VPW; j++) {
-			lo[j] = (warp + FW * j) * Rv;
-			rows[j] = max(0, min(B - lo[j], Rv));
-			wtail[j] = rows[j] > r ? __ldg(&a.weights[lo[j] + r + RG * ((rows[j] - 1 - r) / RG)]) : 0.0f;
-		}
-
-		for (int call = 0; call < a.n_calls; call++) {
-			const int par = call & 1;
-			/* the rows of one warp step can collide in a bank (~3 wavefronts per increment, ncu); private
-			 * replicas per row were tried (2 and 4): what they save here they cost twice in the update */
-			const unsigned hb = cnt_smem_u32(hits + par * cells + cc);
-			float *pl = parts + (size_t)par * 2 * ACC_VW * 32;
-			if (call >= 2)          /* the updaters have consumed (and cleared) this parity's tile */
-				mbar_wait_parity(role_bar + 16 + 8 * par, (unsigned)((call >> 1) - 1) & 1u);
-#pragma unroll
-			for (int j = 0; j < VPW; j++) {
-				const int v = warp + FW * j;
+		/* The (call, virtual warp) pairs of a group of GC calls are dealt round robin to the counter
+		 * warps: pair p = ci * nv + v, warp w takes p = w, w + FW, ...  With B = 256 and GC = 4 every
+		 * warp counts one 64-row run of one of the four calls between two barrier hand-overs. */
+		const int nv = (B + Rv - 1) / Rv;                    /* virtual warps in use, <= ACC_VW */
+		const int n_groups = (a.n_calls + GC - 1) / GC;
+		/* nv divides FW (every case but 16 virtual warps on the 8 counter warps of the slim CTA):
+		 * a warp always meets the same virtual warp, whose run is then loop invariant */
+		const bool vfixed = (FW % nv) == 0;
+		const int lo0 = (warp % nv) * Rv;
+		const int rows0 = min(B - lo0, Rv);
+		const float wtail0 = rows0 > r ? __ldg(&a.weights[lo0 + r + RG * ((rows0 - 1 - r) / RG)]) : 0.0f;
+		for (int grp = 0; grp < n_groups; grp++) {
+			const int par = grp & 1;
+			const int ncg = min(GC, a.n_calls - grp * GC);   /* calls of this group */
+			if (grp >= 2)               /* the updaters have consumed (and cleared) this parity's tiles */
+				mbar_wait_parity(role_bar + 16 + 8 * par, (unsigned)((grp >> 1) - 1) & 1u);
+#pragma unroll 1
+			for (int p = warp; p < ncg * nv; p += FW) {
+				const int ci = p / nv, v = p - ci * nv;
+				const int call = grp * GC + ci;
+				const int tile = par * GC + ci;
+				/* my run: rows [lo, lo + rows) of the call, and the table weight of my last row */
+				int lo = lo0, rows = rows0;
+				float wtail = wtail0;
+				if (!vfixed) {
+					lo = v * Rv;
+					rows = min(B - lo, Rv);
+					wtail = rows > r ? __ldg(&a.weights[lo + r + RG * ((rows - 1 - r) / RG)]) : 0.0f;
+				}
+				/* the rows of one warp step can collide in a bank (~3 wavefronts per increment, ncu); private
+				 * replicas per row were tried (2 and 4): what they save here they cost twice in the update */
+				const unsigned hb = cnt_smem_u32(hits + tile * cells + cc);
+				float *pl = parts + (size_t)tile * 2 * ACC_VW * 32;
 				float acc = 0.0f, mx = -1000.0f;             /* display.cl:91,113 */
 #pragma unroll 1
-				for (int c0 = 0; c0 < rows[j]; c0 += CH) {
+				for (int c0 = 0; c0 < rows; c0 += CH) {
 					if (TMA) {
 						/* rows of the launch are contiguous in the ring: box n holds rows n*BOXR .. */
-						const unsigned g = (unsigned)call * (unsigned)B + (unsigned)(lo[j] + c0);
-						const unsigned n = g / BOXR, slot = n % DEPTH;
-						mbar_wait_parity(full0 + 8u * slot, (n / DEPTH) & 1u);
+						const unsigned g = (unsigned)call * (unsigned)B + (unsigned)(lo + c0);
+						const unsigned n = g / BOXR, slot = n & (DEPTH - 1u);
+						mbar_wait_parity(full0 + 8u * slot, (n >> dlog) & 1u);
 						const float *bp = stage + (size_t)slot * (BOXR * COLS) + (g % BOXR) * COLS + lane;
 #pragma unroll 1
 						for (int s0 = 0; s0 < CH; s0 += SUBR, bp += SUBR * COLS) {
@@ -781,8 +821,8 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 							mbar_arrive(empty0 + 8u * slot);
 					} else {
 						const unsigned ring = (unsigned)a.wf_pos + (unsigned)call * (unsigned)B;
-						const int s0 = lo[j] + c0;
-						const int lim = lo[j] + rows[j];
+						const int s0 = lo + c0;
+						const int lim = lo + rows;
 						float pw[SSTEPS];
 #pragma unroll
 						for (int i = 0; i < SSTEPS; i++) {
@@ -800,7 +840,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 						}
 					}
 				}
-				pl[v * 32 + lane] = __fmul_rn(acc, wtail[j]);
+				pl[v * 32 + lane] = __fmul_rn(acc, wtail);
 				pl[ACC_VW * 32 + v * 32 + lane] = mx;
 			}
 			__syncwarp();           /* orders every lane's increments and partials before the arrive */
@@ -814,42 +854,56 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 		float4 *h4 = reinterpret_cast<float4 *>(hist_s);
 		const float2 *lut = B <= ACC_LUT_MAX ? lut_s : a.lut;
 
-		for (int call = 0; call < a.n_calls; call++) {
-			const int par = call & 1;
-			mbar_wait_parity(role_bar + 8 * par, (unsigned)(call >> 1) & 1u);
+		const int n_groups = (a.n_calls + GC - 1) / GC;
+		for (int grp = 0; grp < n_groups; grp++) {
+			const int par = grp & 1;
+			const int ncg = min(GC, a.n_calls - grp * GC);       /* calls of this group */
+			mbar_wait_parity(role_bar + 8 * par, (unsigned)(grp >> 1) & 1u);
 			/* ---- rise / decay of the tile's cells, display.cl:217-254 ---- */
-			uint4 *hc4 = reinterpret_cast<uint4 *>(hits + par * cells);
+			uint4 *hc4 = reinterpret_cast<uint4 *>(hits + (size_t)par * GC * cells);
 			constexpr int UNR = 2;
 			for (int g0 = ut; g0 < cells / 4; g0 += UT * UNR) {
-				uint4 hc[UNR];
+				uint4 hc[UNR][GC];
 				float4 hv[UNR];
 #pragma unroll
 				for (int u = 0; u < UNR; u++) {
 					const int g = g0 + u * UT;
 					if (g < cells / 4) {
-						hc[u] = hc4[g];
 						hv[u] = h4[g];
+#pragma unroll
+						for (int ci = 0; ci < GC; ci++)
+							hc[u][ci] = hc4[ci * (cells / 4) + g];
 					} else {
-						hc[u] = make_uint4(0u, 0u, 0u, 0u);
 						hv[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+						for (int ci = 0; ci < GC; ci++)
+							hc[u][ci] = make_uint4(0u, 0u, 0u, 0u);
 					}
 				}
 #pragma unroll
 				for (int u = 0; u < UNR; u++) {
 					const int g = g0 + u * UT;
-					const bool hit = (hc[u].x | hc[u].y | hc[u].z | hc[u].w) != 0u;
-					if (hit)
-						hc4[g] = make_uint4(0u, 0u, 0u, 0u);
-					if (hit || fmaxf(fmaxf(hv[u].x, hv[u].y), fmaxf(hv[u].z, hv[u].w)) > 0.01f) {
-						hv[u].x = rise_decay(hv[u].x, hc[u].x, lut);
-						hv[u].y = rise_decay(hv[u].y, hc[u].y, lut);
-						hv[u].z = rise_decay(hv[u].z, hc[u].z, lut);
-						hv[u].w = rise_decay(hv[u].w, hc[u].w, lut);
-						h4[g] = hv[u];
+					bool touched = false;
+#pragma unroll
+					for (int ci = 0; ci < GC; ci++) {
+						if (ci < ncg) {      /* tiles past the last call are all zero and must not decay the cells */
+							const bool hit = (hc[u][ci].x | hc[u][ci].y | hc[u][ci].z | hc[u][ci].w) != 0u;
+							if (hit)
+								hc4[ci * (cells / 4) + g] = make_uint4(0u, 0u, 0u, 0u);
+							if (hit || fmaxf(fmaxf(hv[u].x, hv[u].y), fmaxf(hv[u].z, hv[u].w)) > 0.01f) {
+								hv[u].x = rise_decay(hv[u].x, hc[u][ci].x, lut);
+								hv[u].y = rise_decay(hv[u].y, hc[u][ci].y, lut);
+								hv[u].z = rise_decay(hv[u].z, hc[u][ci].z, lut);
+								hv[u].w = rise_decay(hv[u].w, hc[u][ci].w, lut);
+								touched = true;
+							}
+						}
 					}
+					if (touched)
+						h4[g] = hv[u];
 				}
 			}
-			__syncwarp();           /* all lanes done with this parity's tile */
+			__syncwarp();           /* all lanes done with this parity's tiles */
 			if (lane == 0)
 				mbar_arrive(role_bar + 16 + 8 * par);
 		}
@@ -873,18 +927,22 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 			m = a.spectrum[N + di].y;
 		}
 		for (int call = 0; call < a.n_calls; call++) {
-			const int par = call & 1;
-			mbar_wait_parity(role_bar + 8 * par, (unsigned)(call >> 1) & 1u);
-			const float *pl = parts + (size_t)par * 2 * ACC_VW * 32;
+			const int grp = call / GC, ci = call % GC, par = grp & 1;
+			const bool last_of_group = ci == GC - 1 || call == a.n_calls - 1;
+			if (ci == 0)
+				mbar_wait_parity(role_bar + 8 * par, (unsigned)(grp >> 1) & 1u);
+			const float *pl = parts + (size_t)(par * GC + ci) * 2 * ACC_VW * 32;
 			float pv[ACC_VW], pm[ACC_VW];
 #pragma unroll
 			for (int w = 0; w < ACC_VW; w++) {
 				pv[w] = pl[w * 32 + lane];
 				pm[w] = pl[ACC_VW * 32 + w * 32 + lane];
 			}
-			__syncwarp();           /* partials are in registers: hand the buffer back early */
-			if (lane == 0)
-				mbar_arrive(role_bar + 16 + 8 * par);
+			if (last_of_group) {
+				__syncwarp();       /* partials are in registers: hand the buffers back early */
+				if (lane == 0)
+					mbar_arrive(role_bar + 16 + 8 * par);
+			}
 			float sum = 0.0f, bmax = -1000.0f;
 #pragma unroll
 			for (int w = 0; w < ACC_VW; w++) {
@@ -916,9 +974,9 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 			const unsigned total = (unsigned)a.n_calls * (unsigned)(B / BOXR);
 			const unsigned stage0 = cnt_smem_u32(stage);
 			for (unsigned n = 0; n < total; n++) {
-				const unsigned slot = n % DEPTH;
-				if (n >= (unsigned)DEPTH)
-					mbar_wait_parity(empty0 + 8u * slot, ((n / DEPTH) - 1u) & 1u);
+				const unsigned slot = n & (DEPTH - 1u);
+				if (n >= DEPTH)
+					mbar_wait_parity(empty0 + 8u * slot, ((n >> dlog) - 1u) & 1u);
 				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
 				             ::"r"(full0 + 8u * slot), "r"((unsigned)C::BOX_BYTES) : "memory");
 				tma_load_2d(stage0 + slot * (unsigned)C::BOX_BYTES, &tmap, col0,

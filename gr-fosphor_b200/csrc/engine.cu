@@ -53,6 +53,7 @@ struct fosphor_cu {
 	int log2n = 0;
 	int device = 0;
 	int sm_count = 0;
+	size_t smem_optin = 0;               /* largest dynamic shared memory a CTA may ask for */
 
 	cudaStream_t own_stream = nullptr;
 	cudaStream_t stream = nullptr;       /* FFT kernel, copies to the host, everything the caller orders against */
@@ -88,7 +89,9 @@ struct fosphor_cu {
 	                                      * bin count (measured: cfg2 +14 %, cfg4 +9 %, N=512 sweep +10 %), split
 	                                      * when the per-call state update dominates (cfg3: B = K/2, even) */
 	int chunk_calls = 0;                 /* env FOSPHOR_B200_CHUNK_CALLS: cap on the calls folded per launch (0 = ring) */
-	int acc_roles = 0;                   /* env FOSPHOR_B200_ACC_ROLES: counter/updater warps 1 = 16/8, 2 = 8/16, 3 = 4/16; 0 = by shape */
+	int acc_roles = 0;                   /* env FOSPHOR_B200_ACC_ROLES: counter / updater warps 1 = 16/8, 2 = 8/16 (4-call groups only); 0 = by shape */
+	int acc_stage_kb = 0;                /* env FOSPHOR_B200_ACC_STAGE_KB: cap of the fused kernel's stage ring (0 = what fits) */
+	int acc_group = 0;                   /* env FOSPHOR_B200_ACC_GROUP: calls per counter -> updater hand-over (1 | 2 | 4); 0 = by batch size */
 	int acc_cols = 8;                    /* columns per CTA of the fused kernel (env FOSPHOR_B200_ACC_COLS: 4 | 8) */
 	int acc_box_max = 256;               /* largest TMA box in rows (env FOSPHOR_B200_ACC_BOX: 0 (plain loads) | 16 | 64 | 256) */
 	int acc_sub_max = 64;                /* rows per unrolled body (env FOSPHOR_B200_ACC_SUB: 16 | 64) */
@@ -434,34 +437,54 @@ constexpr int ACC_UW = 8;         /* updater warps of the fused accumulate kerne
 constexpr int ACC_FW_SLIM = 8;    /* counter / updater warps of the slim variant that runs beside the FFT kernel: */
 constexpr int ACC_UW_SLIM = 4;    /* 14 warps x 48 registers fit next to two FFT CTAs (2 x 4 warps x 168 registers)  */
 
-template <int COLS, int FW, int UW, int BOXR, int SUBR, int LOAD>
-cudaError_t fused_launch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st)
+template <int COLS, int FW, int UW, int BOXR, int SUBR, int LOAD, int GC>
+cudaError_t fused_launch(fosphor_cu *e, AccumArgs a, cudaStream_t st)
 {
-	using C = FusedCfg<COLS, FW, UW, BOXR>;
-	const size_t smem = C::smem(a.n_bins, a.batch, LOAD != 0);
+	using C = FusedCfg<COLS, FW, UW, BOXR, GC>;
+	/* stage ring: as many boxes as the SM has room for (FOSPHOR_B200_ACC_STAGE_KB caps it), never more than the launch has */
+	size_t limit = e->smem_optin;
+	if (e->acc_stage_kb > 0 && C::smem_fixed(a.n_bins, a.batch) + (size_t)e->acc_stage_kb * 1024 < limit)
+		limit = C::smem_fixed(a.n_bins, a.batch) + (size_t)e->acc_stage_kb * 1024;
+	int dlog = C::depth_log2(a.n_bins, a.batch, limit);
+	const long long boxes = (long long)a.n_calls * (a.batch / BOXR);
+	while (dlog > 0 && (1ll << (dlog - 1)) >= boxes)
+		dlog--;
+	a.depth_log2 = dlog;
+	const size_t smem = C::smem(a.n_bins, a.batch, LOAD != 0, dlog);
 	static size_t configured = 0;          /* per kernel instantiation */
 	if (smem > configured) {
-		cudaError_t err = cudaFuncSetAttribute(accumulate_fused_kernel<COLS, FW, UW, BOXR, SUBR, LOAD>,
+		cudaError_t err = cudaFuncSetAttribute(accumulate_fused_kernel<COLS, FW, UW, BOXR, SUBR, LOAD, GC>,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (err != cudaSuccess)
 			return err;
 		configured = smem;
 	}
 	const CUtensorMap &tm = e->acc_tmap[BOXR == 256 ? 2 : (BOXR == 64 ? 1 : 0)];
-	accumulate_fused_kernel<COLS, FW, UW, BOXR, SUBR, LOAD><<<a.n / COLS, C::THREADS, smem, st>>>(a, tm);
+	accumulate_fused_kernel<COLS, FW, UW, BOXR, SUBR, LOAD, GC><<<a.n / COLS, C::THREADS, smem, st>>>(a, tm);
 	return cudaGetLastError();
 }
 
-template <int COLS, int FW, int UW>
+template <int COLS, int FW, int UW, int GC = 1>
 cudaError_t fused_dispatch(fosphor_cu *e, const AccumArgs &a, cudaStream_t st, int boxr, int subr)
 {
 	if (boxr == 256)
-		return subr == 64 ? fused_launch<COLS, FW, UW, 256, 64, 1>(e, a, st) : fused_launch<COLS, FW, UW, 256, 16, 1>(e, a, st);
+		return subr == 64 ? fused_launch<COLS, FW, UW, 256, 64, 1, GC>(e, a, st) : fused_launch<COLS, FW, UW, 256, 16, 1, GC>(e, a, st);
 	if (boxr == 64)
-		return subr == 64 ? fused_launch<COLS, FW, UW, 64, 64, 1>(e, a, st) : fused_launch<COLS, FW, UW, 64, 16, 1>(e, a, st);
+		return subr == 64 ? fused_launch<COLS, FW, UW, 64, 64, 1, GC>(e, a, st) : fused_launch<COLS, FW, UW, 64, 16, 1, GC>(e, a, st);
 	if (boxr == 16)
-		return fused_launch<COLS, FW, UW, 16, 16, 1>(e, a, st);
-	return fused_launch<COLS, FW, UW, 16, 16, 0>(e, a, st);
+		return fused_launch<COLS, FW, UW, 16, 16, 1, GC>(e, a, st);
+	return fused_launch<COLS, FW, UW, 16, 16, 0, GC>(e, a, st);
+}
+
+/* shared memory of the fused kernel for a shape with a minimal stage ring (two 256-row boxes) */
+template <int COLS>
+size_t fused_smem_need(int n_bins, int batch, int gc)
+{
+	if (gc == 4)
+		return FusedCfg<COLS, 16, ACC_UW, 256, 4>::smem(n_bins, batch, true, 1);
+	if (gc == 2)
+		return FusedCfg<COLS, 16, ACC_UW, 256, 2>::smem(n_bins, batch, true, 1);
+	return FusedCfg<COLS, 16, ACC_UW, 256, 1>::smem(n_bins, batch, true, 1);
 }
 
 /* one launch: count + rise/decay + live + max-hold of n_calls calls */
@@ -507,22 +530,34 @@ int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st
 	const bool slim = e->two_streams_now && e->acc_slim;
 	if (slim)
 		subr = 16;      /* 46 registers (the 64-row body needs 56): 14 warps fit beside two FFT CTAs */
-	/* warp roles: counters / cell updaters.  The update of a call is K*COLS cells, the count
-	 * B*COLS samples: with few rows per call (B < 2K) the cell updaters are the critical path
-	 * and get the larger share of the CTA. */
+	/* calls per synchronisation group: with few rows per call the barrier round trips between
+	 * counter and updater warps set the pace, so small batches hand over 2 or 4 calls at a time
+	 * (transport only: same per-cell and per-column operation order) */
+	int gc = e->acc_group;
+	if (gc == 0)
+		gc = batch <= 256 ? 4 : 1;        /* measured: cfg3 (B = 256) 115 -> 105 us per 32 calls; B = 1024 prefers the deeper stage ring */
+	const size_t smem_max = e->smem_optin;
+	while (gc > 1 && (e->acc_cols == 4 ? fused_smem_need<4>(a.n_bins, batch, gc)
+	                                   : fused_smem_need<8>(a.n_bins, batch, gc)) > smem_max)
+		gc >>= 1;
+	/* warp roles (counters / cell updaters): 16 / 8, or 8 / 16 when a call has more cells to update
+	 * than rows to count (ncu of cfg3, B = 256, K = 512: the counter warps spent half their time
+	 * waiting for the updaters to hand the hit tiles back) */
 	int roles = e->acc_roles;
 	if (roles == 0)
-		roles = 2 * a.n_bins > batch ? 2 : 1;
+		roles = (gc == 4 && a.n_bins >= batch) ? 2 : 1;
 	if (e->acc_cols == 4)
 		err = slim ? fused_dispatch<4, ACC_FW_SLIM, ACC_UW_SLIM>(e, a, st, boxr, subr)
-		    : roles == 2 ? fused_dispatch<4, 8, 16>(e, a, st, boxr, subr)
-		    : roles == 3 ? fused_dispatch<4, 4, 16>(e, a, st, boxr, subr)
-		                 : fused_dispatch<4, 16, ACC_UW>(e, a, st, boxr, subr);
+		    : gc == 4 ? (roles == 2 ? fused_dispatch<4, 8, 16, 4>(e, a, st, boxr, subr)
+		                            : fused_dispatch<4, 16, ACC_UW, 4>(e, a, st, boxr, subr))
+		    : gc == 2 ? fused_dispatch<4, 16, ACC_UW, 2>(e, a, st, boxr, subr)
+		              : fused_dispatch<4, 16, ACC_UW, 1>(e, a, st, boxr, subr);
 	else
 		err = slim ? fused_dispatch<8, ACC_FW_SLIM, ACC_UW_SLIM>(e, a, st, boxr, subr)
-		    : roles == 2 ? fused_dispatch<8, 8, 16>(e, a, st, boxr, subr)
-		    : roles == 3 ? fused_dispatch<8, 4, 16>(e, a, st, boxr, subr)
-		                 : fused_dispatch<8, 16, ACC_UW>(e, a, st, boxr, subr);
+		    : gc == 4 ? (roles == 2 ? fused_dispatch<8, 8, 16, 4>(e, a, st, boxr, subr)
+		                            : fused_dispatch<8, 16, ACC_UW, 4>(e, a, st, boxr, subr))
+		    : gc == 2 ? fused_dispatch<8, 16, ACC_UW, 2>(e, a, st, boxr, subr)
+		              : fused_dispatch<8, 16, ACC_UW, 1>(e, a, st, boxr, subr);
 	prof_mark(e, 1, 1, st);
 	e->launches++;
 	CU_CHECK(e, err);
@@ -537,7 +572,7 @@ int launch_accumulate(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cuda
 {
 	/* path choice depends on (B, K) only, never on the ring position or the launch
 	 * folding: the two paths add the live spectrum in different orders */
-	if (e->acc_mode > 0 || (e->acc_mode < 0 && batch >= e->p.n_bins && (batch % 16) == 0 && e->acc_tmap_ok))
+	if (e->acc_mode > 0 || (e->acc_mode < 0 && 2 * batch >= e->p.n_bins && (batch % 16) == 0 && e->acc_tmap_ok))
 		return launch_accumulate_fused(e, t, st, count_done, wf_pos, n_calls, batch);
 	AccumArgs a;
 	a.wf = e->d_wf;
@@ -831,6 +866,7 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 		return -ENODEV;
 	}
 	e->sm_count = prop.multiProcessorCount;
+	e->smem_optin = prop.sharedMemPerBlockOptin;
 	CREATE_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
 	e->stream = e->own_stream;
 	CREATE_CHECK(cudaStreamCreateWithFlags(&e->acc_stream, cudaStreamNonBlocking));
@@ -849,6 +885,10 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 		e->acc_slim = atoi(v);
 	if (const char *v = getenv("FOSPHOR_B200_ACC_ROLES"))
 		e->acc_roles = atoi(v);
+	if (const char *v = getenv("FOSPHOR_B200_ACC_STAGE_KB"))
+		e->acc_stage_kb = atoi(v);
+	if (const char *v = getenv("FOSPHOR_B200_ACC_GROUP"))
+		e->acc_group = (atoi(v) == 1 || atoi(v) == 2 || atoi(v) == 4) ? atoi(v) : 0;
 
 	const size_t n = p.fft_len, k = p.n_bins, w = p.wf_rows;
 	CREATE_CHECK(cudaMalloc(&e->d_win, sizeof(float) * n));

@@ -282,16 +282,18 @@ def test_kernel_variants_are_bit_identical(torch_cuda, monkeypatch):
     split count/update kernels sum the live spectrum in another order: histogram and
     waterfall still bit-identical, live/max within the parity tolerance."""
     torch = torch_cuda
-    names = ("FFT_VARIANT", "OVERLAP", "ACC", "ACC_BOX", "ACC_SUB", "COUNT_VARIANT", "OVERLAP_CHUNK", "ACC_SLIM")
-    variants = (("2", "0", "1", "256", "64", "1", "16", "1"),     # fused kernel, one stream
-                ("0", "0", "1", "16", "16", "1", "16", "1"),
-                ("1", "1", "1", "64", "64", "1", "2", "1"),       # two streams, slim co-resident accumulate CTAs
-                ("2", "1", "1", "256", "16", "1", "1", "1"),
-                ("2", "1", "1", "256", "64", "1", "1", "0"),      # two streams, full-size accumulate CTAs
-                ("3", "0", "1", "0", "16", "1", "16", "1"),       # plain loads in the fused kernel
-                ("2", "1", "1", "0", "16", "1", "1", "1"),        # ... and in the slim one
-                ("2", "1", "0", "64", "64", "1", "1", "1"),       # split kernels, TMA-staged count
-                ("0", "0", "0", "64", "64", "0", "16", "1"))      # split kernels, plain count
+    names = ("FFT_VARIANT", "OVERLAP", "ACC", "ACC_BOX", "ACC_SUB", "COUNT_VARIANT", "OVERLAP_CHUNK", "ACC_SLIM",
+             "ACC_GROUP")
+    variants = (("2", "0", "1", "256", "64", "1", "16", "1", "1"),     # fused kernel, one stream
+                ("0", "0", "1", "16", "16", "1", "16", "1", "2"),      # calls handed over in pairs
+                ("2", "0", "1", "256", "64", "1", "16", "1", "4"),     # ... in fours (short last group)
+                ("1", "1", "1", "64", "64", "1", "2", "1", "0"),       # two streams, slim co-resident accumulate CTAs
+                ("2", "1", "1", "256", "16", "1", "1", "1", "0"),
+                ("2", "1", "1", "256", "64", "1", "1", "0", "2"),      # two streams, full-size accumulate CTAs
+                ("3", "0", "1", "0", "16", "1", "16", "1", "4"),       # plain loads in the fused kernel
+                ("2", "1", "1", "0", "16", "1", "1", "1", "1"),        # ... and in the slim one
+                ("2", "1", "0", "64", "64", "1", "1", "1", "0"),       # split kernels, TMA-staged count
+                ("0", "0", "0", "64", "64", "0", "16", "1", "0"))      # split kernels, plain count
     for n in (1024, 512, 2048, 4096, 8192):
         calls, b = (5, 1024) if n <= 1024 else (3, 256)
         x = signals.noise_tones(n * b * calls, n_fft=n, seed=77)

@@ -15,7 +15,8 @@ import perf_configs  # noqa: E402
 def main():
     import torch
     shapes = {"cfg2": ("cfg2", 1024, 256, 4, 1024, 64, 32768, False, {}),
-              "cfg3": ("cfg3", 4096, 512, 8, 256, 32, 8192, True, {"t0d": 20.0}),
+              "cfg3": ("cfg3", 4096, 512, 8, 256, 256, 32768, True, {"t0d": 20.0}),
+              "cfg3r8": ("cfg3r8", 4096, 512, 8, 256, 32, 8192, True, {"t0d": 20.0}),
               "cfg4": ("cfg4", 16384, 1024, 1, 1024, 32, 16384, False, {}),
               "cfg4r4": ("cfg4r4", 16384, 1024, 1, 1024, 4, 4096, False, {}),
               "n2048": ("n2048", 2048, 256, 4, 1024, 32, 16384, True, {}),

@@ -102,7 +102,7 @@ def main():
     res.append(run(torch, "cfg2 pre-overlapped", 1024, 256, 4, 1024, 64, 32768, False))
     res.append(run(torch, "cfg2 in-engine overlap", 1024, 256, 4, 1024, 64, 32768, True))
     # cfg3: N=4096, 512 bins, overlap 8, tau=0.95 -> t0d=20, B=256
-    res.append(run(torch, "cfg3 persistence stress", 4096, 512, 8, 256, 32, 8192, True, t0d=20.0))
+    res.append(run(torch, "cfg3 persistence stress", 4096, 512, 8, 256, 256, 32768, True, t0d=20.0))
     # cfg4 shape on one GPU (one channel): N=16384, 1024 bins, B=1024
     res.append(run(torch, "cfg4 one channel", 16384, 1024, 1, 1024, 32, 16384, False))
     # cfg5 sweep: K=256, overlap 4, B=1024
