@@ -556,12 +556,14 @@ constexpr unsigned ACC_WAIT_HINT_NS = 20000u; /* mbarrier.try_wait suspend-time 
 constexpr int ACC_LUT_MAX = 4096; /* batches up to this keep the (d, e) table in shared memory */
 
 template <int COLS>
-__device__ __forceinline__ unsigned bin_cell_offset(float pwr, float hofs, float hscale2, int kmax2)
+__device__ __forceinline__ unsigned bin_cell_addr(float pwr, float hofs, float hscale2, unsigned kmax2, unsigned tile_col)
 {
-	/* see bin_row_offset(): byte offset of hits[bin][0] with COLS u32 per bin */
-	const int i = __float2int_rd(__fmul_rn(hscale2, __fadd_rn(pwr, hofs)));
-	const int j = min(max(i, -1), kmax2) + 1;        /* 0 .. 2*kmax + 1 */
-	return ((unsigned)j & ~1u) * (COLS * 2);         /* (j >> 1) * COLS * 4 */
+	/* see bin_row_offset().  Shared-memory byte address of hits[bin][col], COLS u32 per bin, for a tile
+	 * aligned to its size; tile_col = tile base | col * 4.  The UNSIGNED floor conversion saturates:
+	 * t < 0 (floor = -1 -> bin 0), NaN and -inf give 0 -> bin 0, +inf gives UINT_MAX -> kmax2 ->
+	 * bin K-1; then bin = (i + 1) >> 1, times COLS * 4 bytes, OR-ed into the tile address (one LOP3). */
+	const unsigned i = min(__float2uint_rd(__fmul_rn(hscale2, __fadd_rn(pwr, hofs))), kmax2);
+	return (((i + 1u) * (COLS * 2)) & ~(unsigned)(COLS * 4 - 1)) | tile_col;
 }
 
 /* rows per virtual warp and call: contiguous runs, at least 64 rows so that the per-run
@@ -593,6 +595,16 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar)
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+/* A hit tile starts at a multiple of its (power of two) size, so that the byte address of
+ * hits[bin][col] is  tile | bin_offset | col*4  - one LOP3 - instead of an addition. */
+__host__ __device__ inline unsigned acc_tile_bytes(int K, int cols)
+{
+	unsigned a = 128;
+	while (a < (unsigned)(K * cols) * 4u)
+		a <<= 1;
+	return a;
+}
+
 template <int COLS, int FW, int UW, int BOXR, int GC = 1>
 struct FusedCfg {
 	static_assert(GC == 1 || GC == 2 || GC == 4, "calls per synchronisation group");
@@ -612,7 +624,8 @@ struct FusedCfg {
 	static size_t smem_fixed(int K, int batch)
 	{
 		size_t bar = (BAR_BYTES + 127) & ~(size_t)127;
-		return bar + PART_BYTES + sizeof(float) * (2 * GC + 1) * (size_t)K * COLS +
+		/* state tile, 2*GC hit tiles at tile-size granularity + the worst-case alignment gap */
+		return bar + PART_BYTES + sizeof(float) * (size_t)K * COLS + (size_t)acc_tile_bytes(K, COLS) * (2 * GC + 1) +
 		       (batch <= ACC_LUT_MAX ? sizeof(float2) * (size_t)(batch + 1) : 0) + 128;
 	}
 	/* The stage ring is what keeps HBM busy: one CTA per SM, so bytes in flight per SM = the ring
@@ -701,11 +714,16 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 	sp += (C::BAR_BYTES + 127) & ~(size_t)127;
 	float *parts = reinterpret_cast<float *>(sp);        /* [2 parity][GC calls][2 live/max][ACC_VW][32] */
 	sp += C::PART_BYTES;
-	unsigned *hits = reinterpret_cast<unsigned *>(sp);   /* [2 parity][GC calls][K][COLS] */
-	sp += sizeof(unsigned) * 2 * GC * (size_t)cells;
 	float *hist_s = reinterpret_cast<float *>(sp);       /* [K][COLS] */
 	sp += sizeof(float) * (size_t)cells;
 	float2 *lut_s = reinterpret_cast<float2 *>(sp);      /* [B+1] (d, e) table when B <= ACC_LUT_MAX */
+	if (B <= ACC_LUT_MAX)
+		sp += (sizeof(float2) * (size_t)(B + 1) + 15) & ~(size_t)15;
+	/* hit tiles [2 parity][GC calls], each [K][COLS] u32 at a multiple of the tile size (a power of two) */
+	const unsigned tile_bytes = acc_tile_bytes(K, COLS);
+	const unsigned tile_words = tile_bytes / 4;
+	sp += (tile_bytes - (cnt_smem_u32(sp) & (tile_bytes - 1))) & (tile_bytes - 1);
+	unsigned *hits = reinterpret_cast<unsigned *>(sp);
 
 	const unsigned full0 = cnt_smem_u32(bars);                   /* full[DEPTH]  */
 	const unsigned empty0 = full0 + 8u * DEPTH;                  /* empty[DEPTH] */
@@ -737,7 +755,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 			const int bin = g / cpr, c4 = (g % cpr) * 4;
 			h4[g] = *reinterpret_cast<const float4 *>(a.hist + (size_t)bin * N + col0 + c4);
 		}
-		for (int g = threadIdx.x; g < 2 * GC * cells / 4; g += WORKERS)
+		for (int g = threadIdx.x; g < 2 * GC * (int)tile_words / 4; g += WORKERS)
 			z4[g] = make_uint4(0u, 0u, 0u, 0u);
 		if (B <= ACC_LUT_MAX)
 			for (int i = threadIdx.x; i <= B; i += WORKERS)
@@ -752,7 +770,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 		/* ================= counter warps ================= */
 		const int r = lane / COLS, cc = lane % COLS;
 		const unsigned mask = (unsigned)a.wf_mask;
-		const int kmax2 = 2 * (K - 1);
+		const unsigned kmax2 = 2u * (unsigned)(K - 1), cc4 = 4u * (unsigned)cc;
 		const float hscale2 = 2.0f * a.hscale;
 		const float hofs = a.hofs;
 		const float rho = a.rho_rg;                          /* (1-alpha)^RG */
@@ -777,7 +795,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 				mbar_wait_parity(role_bar + 16 + 8 * par, (unsigned)((grp >> 1) - 1) & 1u);
 #pragma unroll 1
 			for (int p = warp; p < ncg * nv; p += FW) {
-				const int ci = p / nv, v = p - ci * nv;
+				const int ci = GC == 1 ? 0 : p / nv, v = p - ci * nv;
 				const int call = grp * GC + ci;
 				const int tile = par * GC + ci;
 				/* my run: rows [lo, lo + rows) of the call, and the table weight of my last row */
@@ -790,7 +808,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 				}
 				/* the rows of one warp step can collide in a bank (~3 wavefronts per increment, ncu); private
 				 * replicas per row were tried (2 and 4): what they save here they cost twice in the update */
-				const unsigned hb = cnt_smem_u32(hits + tile * cells + cc);
+				const unsigned hb = cnt_smem_u32(hits + tile * tile_words) | cc4;   /* tile | column: the bin offset is OR-ed in */
 				float *pl = parts + (size_t)tile * 2 * ACC_VW * 32;
 				float acc = 0.0f, mx = -1000.0f;             /* display.cl:91,113 */
 #pragma unroll 1
@@ -811,8 +829,8 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 							for (int i = 0; i < SSTEPS; i++) {
 								acc = fmaf(acc, rho, pw[i]);                      /* display.cl:149-150 (Horner) */
 								mx = fmaxf(mx, pw[i]);                            /* :139 */
-								const unsigned off = bin_cell_offset<COLS>(pw[i], hofs, hscale2, kmax2);   /* :161-165 */
-								asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hb + off) : "memory");    /* :170-177 */
+								const unsigned cell = bin_cell_addr<COLS>(pw[i], hofs, hscale2, kmax2, hb);   /* :161-165 */
+								asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cell) : "memory");       /* :170-177 */
 							}
 						}
 						/* every lane has USED its values: hand the box back */
@@ -834,8 +852,8 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 							if (s0 + RG * i + r < lim) {
 								acc = fmaf(acc, rho, pw[i]);
 								mx = fmaxf(mx, pw[i]);
-								const unsigned off = bin_cell_offset<COLS>(pw[i], hofs, hscale2, kmax2);
-								asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hb + off) : "memory");
+								const unsigned cell = bin_cell_addr<COLS>(pw[i], hofs, hscale2, kmax2, hb);
+								asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cell) : "memory");
 							}
 						}
 					}
@@ -860,7 +878,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 			const int ncg = min(GC, a.n_calls - grp * GC);       /* calls of this group */
 			mbar_wait_parity(role_bar + 8 * par, (unsigned)(grp >> 1) & 1u);
 			/* ---- rise / decay of the tile's cells, display.cl:217-254 ---- */
-			uint4 *hc4 = reinterpret_cast<uint4 *>(hits + (size_t)par * GC * cells);
+			uint4 *hc4 = reinterpret_cast<uint4 *>(hits + (size_t)par * GC * tile_words);
 			constexpr int UNR = 2;
 			for (int g0 = ut; g0 < cells / 4; g0 += UT * UNR) {
 				uint4 hc[UNR][GC];
@@ -872,7 +890,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 						hv[u] = h4[g];
 #pragma unroll
 						for (int ci = 0; ci < GC; ci++)
-							hc[u][ci] = hc4[ci * (cells / 4) + g];
+							hc[u][ci] = hc4[ci * (tile_words / 4) + g];
 					} else {
 						hv[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
@@ -889,7 +907,7 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 						if (ci < ncg) {      /* tiles past the last call are all zero and must not decay the cells */
 							const bool hit = (hc[u][ci].x | hc[u][ci].y | hc[u][ci].z | hc[u][ci].w) != 0u;
 							if (hit)
-								hc4[ci * (cells / 4) + g] = make_uint4(0u, 0u, 0u, 0u);
+								hc4[ci * (tile_words / 4) + g] = make_uint4(0u, 0u, 0u, 0u);
 							if (hit || fmaxf(fmaxf(hv[u].x, hv[u].y), fmaxf(hv[u].z, hv[u].w)) > 0.01f) {
 								hv[u].x = rise_decay(hv[u].x, hc[u][ci].x, lut);
 								hv[u].y = rise_decay(hv[u].y, hc[u][ci].y, lut);
