@@ -745,25 +745,30 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
 	__syncthreads();                /* barriers are live: the producer may start filling the stage ring ... */
-	/* ... while the other warps bring the tile state in, clear the hit tiles and stage the table */
-	constexpr int WORKERS = C::THREADS - 32;     /* every warp but the producer (the last one) */
-	if (threadIdx.x < WORKERS) {
+	/* ... while the counters clear the hit tiles and the updaters bring the tile state and the table
+	 * in: the counters start on the first call without waiting for the state (ncu of cfg4, 16 calls
+	 * per CTA: 10 % of the samples sat on the state load).  Everything the other role reads of these
+	 * buffers is ordered by the cnt_done / hits_free barriers. */
+	if (warp < FW) {
+		uint4 *z4 = reinterpret_cast<uint4 *>(hits);
+		for (int g = threadIdx.x; g < 2 * GC * (int)tile_words / 4; g += FW * 32)
+			z4[g] = make_uint4(0u, 0u, 0u, 0u);
+		/* partials of virtual warps that small batches never visit: 0 / -1000 (display.cl:91,113) */
+		for (int i = threadIdx.x; i < 2 * GC * 2 * ACC_VW * 32; i += FW * 32)
+			parts[i] = ((i / (ACC_VW * 32)) & 1) ? -1000.0f : 0.0f;
+		asm volatile("bar.sync 1, %0;" ::"n"(FW * 32) : "memory");
+	} else if (warp < FW + UW) {
 		constexpr int cpr = COLS / 4;                /* float4 groups per bin row */
 		float4 *h4 = reinterpret_cast<float4 *>(hist_s);
-		uint4 *z4 = reinterpret_cast<uint4 *>(hits);
-		for (int g = threadIdx.x; g < cells / 4; g += WORKERS) {
+		const int ut = threadIdx.x - FW * 32;
+		for (int g = ut; g < cells / 4; g += UW * 32) {
 			const int bin = g / cpr, c4 = (g % cpr) * 4;
 			h4[g] = *reinterpret_cast<const float4 *>(a.hist + (size_t)bin * N + col0 + c4);
 		}
-		for (int g = threadIdx.x; g < 2 * GC * (int)tile_words / 4; g += WORKERS)
-			z4[g] = make_uint4(0u, 0u, 0u, 0u);
 		if (B <= ACC_LUT_MAX)
-			for (int i = threadIdx.x; i <= B; i += WORKERS)
+			for (int i = ut; i <= B; i += UW * 32)
 				lut_s[i] = __ldg(&a.lut[i]);
-		/* partials of virtual warps that small batches never visit: 0 / -1000 (display.cl:91,113) */
-		for (int i = threadIdx.x; i < 2 * GC * 2 * ACC_VW * 32; i += WORKERS)
-			parts[i] = ((i / (ACC_VW * 32)) & 1) ? -1000.0f : 0.0f;
-		asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");
+		asm volatile("bar.sync 2, %0;" ::"n"(UW * 32) : "memory");
 	}
 
 	if (warp < FW) {

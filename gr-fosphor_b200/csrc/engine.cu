@@ -321,6 +321,27 @@ cudaError_t cta_stream_launch(fosphor_cu *e, const float2 *in, long long hop, in
 	return cudaGetLastError();
 }
 
+template <class P>
+cudaError_t half_stage_launch(fosphor_cu *e, const float2 *in, long long hop, int wf_pos, int n_spectra)
+{
+	using C = HalfStageCfg<P>;
+	static bool configured = false;
+	if (!configured) {
+		cudaError_t err = cudaFuncSetAttribute(fft_power_half_stage_kernel<P>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+		if (err != cudaSuccess)
+			return err;
+		configured = true;
+	}
+	const int grid = n_spectra < e->sm_count ? n_spectra : e->sm_count;   /* persistent, one CTA per SM */
+	prof_mark(e, 0, 0);
+	fft_power_half_stage_kernel<P><<<grid, C::THREADS, C::SMEM, e->stream>>>(
+		in, hop, e->d_win, e->d_tw, e->d_wf, wf_pos, e->p.wf_rows - 1, n_spectra);
+	prof_mark(e, 0, 1);
+	e->launches++;
+	return cudaGetLastError();
+}
+
 cudaError_t launch_fft(fosphor_cu *e, const float2 *in, long long hop, int wf_pos, int n_spectra)
 {
 	/* TMA bulk copies need 16-byte aligned spectra */
@@ -333,6 +354,8 @@ cudaError_t launch_fft(fosphor_cu *e, const float2 *in, long long hop, int wf_po
 			return stream_launch<Plan1024>(e, in, hop, wf_pos, n_spectra);
 		if (e->p.fft_len == 512)
 			return stream_launch<Plan512>(e, in, hop, wf_pos, n_spectra);
+		if (e->p.fft_len == 16384 && e->fft_variant >= 2)
+			return half_stage_launch<Plan16384>(e, in, hop, wf_pos, n_spectra);
 		/* The CTA-level streaming kernel measured SLOWER than the plain one (N = 4096:
 		 * 101 vs 86 us per 8192 spectra; fewer resident CTAs outweigh the prefetch), so
 		 * it is only reachable as experiment variant 3. */
@@ -551,12 +574,14 @@ int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st
 		    : gc == 4 ? (roles == 2 ? fused_dispatch<4, 8, 16, 4>(e, a, st, boxr, subr)
 		                            : fused_dispatch<4, 16, ACC_UW, 4>(e, a, st, boxr, subr))
 		    : gc == 2 ? fused_dispatch<4, 16, ACC_UW, 2>(e, a, st, boxr, subr)
+		    : roles == 2 ? fused_dispatch<4, 8, 16, 1>(e, a, st, boxr, subr)
 		              : fused_dispatch<4, 16, ACC_UW, 1>(e, a, st, boxr, subr);
 	else
 		err = slim ? fused_dispatch<8, ACC_FW_SLIM, ACC_UW_SLIM>(e, a, st, boxr, subr)
 		    : gc == 4 ? (roles == 2 ? fused_dispatch<8, 8, 16, 4>(e, a, st, boxr, subr)
 		                            : fused_dispatch<8, 16, ACC_UW, 4>(e, a, st, boxr, subr))
 		    : gc == 2 ? fused_dispatch<8, 16, ACC_UW, 2>(e, a, st, boxr, subr)
+		    : roles == 2 ? fused_dispatch<8, 8, 16, 1>(e, a, st, boxr, subr)
 		              : fused_dispatch<8, 16, ACC_UW, 1>(e, a, st, boxr, subr);
 	prof_mark(e, 1, 1, st);
 	e->launches++;

@@ -68,6 +68,14 @@ __device__ __forceinline__ float log_power(float2 x)
 	return l * FOSPHOR_HALF_LOG10_2;
 }
 
+/* fft.cl:416-417: the windowed sample is an f32 product.  __fmul_rn is never contracted into the
+ * first butterfly's add (a plain * may or may not be, depending on the surrounding kernel), which
+ * keeps every kernel variant bit-identical and matches the oracle's rounded products. */
+__device__ __forceinline__ float2 win_mul(float2 x, float w)
+{
+	return make_float2(__fmul_rn(x.x, w), __fmul_rn(x.y, w));
+}
+
 template <class P>
 __device__ __forceinline__ void sync_spectrum()
 {
@@ -122,7 +130,7 @@ fft_power_kernel(const float2 *__restrict__ in, long long hop,
 		for (int t = 0; t < R0; t++) {
 			const float2 a = x[i + t * P::NB0];
 			const float w = __ldg(&win[i + t * P::NB0]);
-			v[t] = make_float2(a.x * w, a.y * w);   /* fft.cl:416-417 */
+			v[t] = win_mul(a, w);   /* fft.cl:416-417 */
 		}
 		dif<R0>(v);
 		static_for<0, R0>([&](auto tc) {
@@ -342,7 +350,7 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 				for (int t = 0; t < R0; t++) {
 					const float2 x = bq[lane + t * P::NB0];
 					const float w = TWREG ? swin[lane + t * P::NB0] : wreg[t];
-					v0[t] = make_float2(x.x * w, x.y * w);               /* fft.cl:416-417 */
+					v0[t] = win_mul(x, w);               /* fft.cl:416-417 */
 				}
 			}
 			__syncwarp();                   /* inputs consumed: the slot becomes the exchange buffer */
@@ -461,7 +469,7 @@ fft_power_cta_stream_kernel(const float2 *__restrict__ in, long long hop,
 			for (int t = 0; t < R0; t++) {
 				const float2 x = buf[i + t * P::NB0];
 				const float w = __ldg(&win[i + t * P::NB0]);
-				v0[q][t] = make_float2(x.x * w, x.y * w);           /* fft.cl:416-417 */
+				v0[q][t] = win_mul(x, w);           /* fft.cl:416-417 */
 			}
 			dif<R0>(v0[q]);
 		}
@@ -474,6 +482,142 @@ fft_power_cta_stream_kernel(const float2 *__restrict__ in, long long hop,
 				buf[pad_idx<P>(i * R0 + t)] = v0[q][brev<R0>(t)];
 			});
 		}
+		__syncthreads();
+
+		/* ---- pass 1 (P = R0) ---- */
+		const int i = tid;
+		const int k = i & (R0 - 1);
+		float2 v[R1];
+#pragma unroll
+		for (int t = 0; t < R1; t++)
+			v[t] = buf[pad_idx<P>(i + t * P::NB1)];
+#pragma unroll
+		for (int t = 1; t < R1; t++)
+			v[t] = cmul(v[t], __ldg(&tw[t * R0 + k]));
+		dif<R1>(v);
+		const int j = (i - k) * R1 + k;
+		__syncthreads();
+		static_for<0, R1>([&](auto tc) {
+			constexpr int t = decltype(tc)::value;
+			buf[pad_idx<P>(j + t * R0)] = v[brev<R1>(t)];
+		});
+		__syncthreads();
+
+		/* ---- pass 2 (P = R0 * R1), last ---- */
+		constexpr int P2 = R0 * R1;
+		const int k2 = i & (P2 - 1);
+#pragma unroll
+		for (int t = 0; t < R1; t++)
+			v[t] = buf[pad_idx<P>(i + t * P::NB1)];
+#pragma unroll
+		for (int t = 1; t < R1; t++)
+			v[t] = cmul(v[t], __ldg(&tw[P::TW1 + t * P2 + k2]));
+		dif<R1>(v);
+		static_for<0, R1>([&](auto tc) {
+			constexpr int t = decltype(tc)::value;
+			row[i + t * P::NB1] = log_power(v[brev<R1>(t)]);
+		});
+	}
+}
+
+/* ------------------------------------------------------------------------ */
+/* Half-staged persistent variant for N = 16384                               */
+/* ------------------------------------------------------------------------ */
+/*
+ * The exchange buffer of a 16384-point spectrum is 136 KB: one CTA per SM, no room for a
+ * second input buffer, and the plain kernel serialises "load 128 KB" and "transform" (ncu:
+ * 47 % issue, 35 % of HBM peak).  Here the CTA is persistent and the 64 KB of shared memory
+ * that are left stage HALF of the next spectrum - the inputs of pass-0 butterflies 0..511,
+ * sixteen 4 KB runs - through the TMA engine while the current spectrum is transformed.
+ * The other half is loaded straight into registers at the top of the iteration (the whole
+ * next spectrum was pulled into L2 one iteration earlier) and arrives while the staged half
+ * is being transformed.  Same arithmetic as fft_power_kernel: bit-identical rows.
+ */
+template <class P>
+struct HalfStageCfg {
+	static_assert(P::NPASS == 3 && P::NB0 == 2 * P::T, "two pass-0 butterflies per thread");
+	static constexpr int THREADS = P::T;
+	static constexpr int STG_ELEMS = P::R0 * P::T;                 /* float2: [R0][T] */
+	static constexpr unsigned RUN_BYTES = sizeof(float2) * P::T;  /* one contiguous run of the staged half */
+	static constexpr size_t SMEM = sizeof(float2) * ((size_t)P::SM_ELEMS + STG_ELEMS) + 16;
+};
+
+template <class P>
+__global__ void __launch_bounds__(HalfStageCfg<P>::THREADS, 1)
+fft_power_half_stage_kernel(const float2 *__restrict__ in, long long hop,
+                            const float *__restrict__ win, const float2 *__restrict__ tw,
+                            float *__restrict__ wf, int wf_pos, int wf_mask, int n_spectra)
+{
+	using C = HalfStageCfg<P>;
+	constexpr int N = P::N, R0 = P::R0, R1 = P::R1, T = P::T;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float2 *buf = reinterpret_cast<float2 *>(smem_raw);                  /* padded exchange buffer */
+	float2 *stg = buf + P::SM_ELEMS;                                     /* staged half: [R0][T] */
+	const unsigned stg0 = smem_u32(stg);
+	const unsigned bar = smem_u32(smem_raw + sizeof(float2) * ((size_t)P::SM_ELEMS + C::STG_ELEMS));
+	const int tid = threadIdx.x;
+
+	auto request = [&](int s) {             /* thread 0: staged half of spectrum s, and all of it into L2 */
+		const float2 *x = in + (long long)s * hop;
+		asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x), "r"((unsigned)(sizeof(float2) * N)) : "memory");
+		mbar_expect_tx(bar, C::RUN_BYTES * R0);
+#pragma unroll 1
+		for (int t = 0; t < R0; t++)
+			bulk_g2s(stg0 + (unsigned)t * C::RUN_BYTES, x + t * P::NB0, C::RUN_BYTES, bar);
+	};
+
+	if (tid == 0) {
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		if ((int)blockIdx.x < n_spectra)
+			request(blockIdx.x);
+	}
+	__syncthreads();
+
+	unsigned phase = 0u;
+	for (int s = blockIdx.x; s < n_spectra; s += gridDim.x) {
+		const float2 *x = in + (long long)s * hop;
+		float *row = wf + (size_t)((wf_pos + s) & wf_mask) * N;
+
+		/* ---- pass 0, second butterfly (i = tid + T): inputs straight from L2 into registers ---- */
+		float2 vb[R0];
+#pragma unroll
+		for (int t = 0; t < R0; t++)
+			vb[t] = __ldcg(&x[tid + T + t * P::NB0]);
+
+		/* ---- pass 0, first butterfly (i = tid): inputs from the staged half ---- */
+		while (!mbar_try_wait(bar, phase)) { }
+		phase ^= 1u;
+		float2 va[R0];
+#pragma unroll
+		for (int t = 0; t < R0; t++) {
+			const float2 a = stg[t * T + tid];
+			const float w = __ldg(&win[tid + t * P::NB0]);
+			va[t] = win_mul(a, w);                   /* fft.cl:416-417 */
+		}
+		/* everybody has read the staged half, and everybody is past the pass-2 reads of the previous
+		 * spectrum: refill the stage, overwrite the exchange buffer */
+		__syncthreads();
+		if (tid == 0 && s + (int)gridDim.x < n_spectra) {
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			request(s + gridDim.x);
+		}
+		dif<R0>(va);
+		static_for<0, R0>([&](auto tc) {
+			constexpr int t = decltype(tc)::value;
+			buf[pad_idx<P>(tid * R0 + t)] = va[brev<R0>(t)];
+		});
+#pragma unroll
+		for (int t = 0; t < R0; t++) {
+			const float w = __ldg(&win[tid + T + t * P::NB0]);
+			vb[t] = win_mul(vb[t], w);
+		}
+		dif<R0>(vb);
+		static_for<0, R0>([&](auto tc) {
+			constexpr int t = decltype(tc)::value;
+			buf[pad_idx<P>((tid + T) * R0 + t)] = vb[brev<R0>(t)];
+		});
 		__syncthreads();
 
 		/* ---- pass 1 (P = R0) ---- */

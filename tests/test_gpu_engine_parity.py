@@ -276,7 +276,7 @@ def test_n512_pairs_with_odd_spectrum_counts(torch_cuda):
 
 def test_kernel_variants_are_bit_identical(torch_cuda, monkeypatch):
     """Transport variants must not change a single bit: TMA-prefetching FFT kernels
-    (warp-level for N = 512/1024, CTA-level for 2048/4096/8192) vs plain; fused
+    (warp-level for N = 512/1024, CTA-level for 2048/4096/8192, half-staged for 16384) vs plain; fused
     accumulate kernel with 256/64/16-row TMA boxes vs plain loads;
     two-stream overlap vs one stream (several calls folded per launch).  The older
     split count/update kernels sum the live spectrum in another order: histogram and
@@ -294,7 +294,7 @@ def test_kernel_variants_are_bit_identical(torch_cuda, monkeypatch):
                 ("2", "1", "1", "0", "16", "1", "1", "1", "1"),        # ... and in the slim one
                 ("2", "1", "0", "64", "64", "1", "1", "1", "0"),       # split kernels, TMA-staged count
                 ("0", "0", "0", "64", "64", "0", "16", "1", "0"))      # split kernels, plain count
-    for n in (1024, 512, 2048, 4096, 8192):
+    for n in (1024, 512, 2048, 4096, 8192, 16384):
         calls, b = (5, 1024) if n <= 1024 else (3, 256)
         x = signals.noise_tones(n * b * calls, n_fft=n, seed=77)
         d = _to_dev(torch, x)
