@@ -379,7 +379,7 @@ def run_b200(args):
                          "peak_source": peak_src, "traffic": traffic,
                          "bytes_per_launch": fft_bytes, "ms_per_launch": fft_ms,
                          "spectra_per_launch": spectra_per_fft_launch,
-                         "accumulate_kernel": "accumulate_fused_kernel<8,16,4,64,TMA> (count + rise/decay + live + max-hold, one launch)",
+                         "accumulate_kernel": "accumulate_fused_kernel<COLS=8, 16 counter + 8 updater warps, 256-row TMA boxes> (count + rise/decay + live + max-hold, one launch)",
                          "accumulate_ms_per_launch": count_ms + update_ms,
                          "step_algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                          "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},

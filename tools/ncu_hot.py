@@ -12,6 +12,13 @@ def main():
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
     raw = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv"], stderr=subprocess.DEVNULL).decode()
     rows = list(csv.reader(io.StringIO(raw)))
+    # one segment per kernel: a "Kernel Name" row, a header row, then the SASS lines
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+    for a, b in zip(starts[:-1], starts[1:]):
+        report(rows[a:b], top)
+
+
+def report(rows, top):
     hdr = rows[1]
     print(rows[0][1][:120])
     isrc, ie, iss = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
@@ -33,6 +40,7 @@ def main():
     for d in sorted(data, key=lambda d: -d[3])[:top]:
         print("%5d %-70s exec %9d  samples %6d %5.1f%%  %s" % (d[0], d[1][:70], d[2], d[3], 100.0 * d[3] / max(1, tot_s),
               " ".join("%s:%d" % (n, c) for c, n in d[4] if c)))
+    print()
 
 
 if __name__ == "__main__":
