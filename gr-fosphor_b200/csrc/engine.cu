@@ -53,6 +53,7 @@ struct fosphor_cu {
 	int log2n = 0;
 	int device = 0;
 	int sm_count = 0;
+	int await_slot = -1;                 /* staging slot whose H2D copy from caller memory the current call still has to wait for */
 	size_t smem_optin = 0;               /* largest dynamic shared memory a CTA may ask for */
 
 	cudaStream_t own_stream = nullptr;
@@ -760,9 +761,13 @@ int upload_staged(fosphor_cu *e, const float2 *src, size_t n_samples, float2 **d
 	const size_t bytes = sizeof(float2) * n_samples;
 	CU_CHECK(e, cudaEventSynchronize(e->slot_free[s]));     /* previous reader of d_in[s] done */
 	if (is_pinned_host(src)) {
+		/* DMA straight from the caller's page-locked memory.  The caller may recycle it as soon as the
+		 * process call returns (base_sink_c_impl.cc:170-174), so the call waits for this copy - but
+		 * only at its very end (await_uploads), after the kernels that consume it were enqueued behind
+		 * the `copied` event: the launch overhead hides under the copy instead of following it. */
 		CU_CHECK(e, cudaMemcpyAsync(e->d_in[s], src, bytes, cudaMemcpyHostToDevice, e->copy_stream));
 		CU_CHECK(e, cudaEventRecord(e->copied[s], e->copy_stream));
-		CU_CHECK(e, cudaEventSynchronize(e->copied[s]));
+		e->await_slot = s;
 	} else {
 		memcpy(e->h_in[s], src, bytes);
 		CU_CHECK(e, cudaMemcpyAsync(e->d_in[s], e->h_in[s], bytes, cudaMemcpyHostToDevice, e->copy_stream));
@@ -771,6 +776,18 @@ int upload_staged(fosphor_cu *e, const float2 *src, size_t n_samples, float2 **d
 	CU_CHECK(e, cudaStreamWaitEvent(e->stream, e->copied[s], 0));
 	e->last_slot = s;
 	*dev_out = e->d_in[s];
+	return 0;
+}
+
+/* the caller's page-locked samples have been read (the copy stream is in order: the last copy
+ * issued is the last to complete) */
+int await_uploads(fosphor_cu *e)
+{
+	if (e->await_slot >= 0) {
+		const int s = e->await_slot;
+		e->await_slot = -1;
+		CU_CHECK(e, cudaEventSynchronize(e->copied[s]));
+	}
 	return 0;
 }
 
@@ -1119,9 +1136,10 @@ int fosphor_cu_process_host(struct fosphor_cu *e, const void *samples_host, int 
 			return rc;
 	}
 	int rc = process_device_calls(e, dev, 1, len / n, n);
-	if (rc)
-		return rc;
-	return release_slot(e);
+	if (!rc)
+		rc = release_slot(e);
+	const int rc2 = await_uploads(e);     /* also on the error path: the source is the caller's again on return */
+	return rc ? rc : rc2;
 }
 
 int fosphor_cu_process_host_raw(struct fosphor_cu *e, const void *raw_host,
@@ -1144,16 +1162,16 @@ int fosphor_cu_process_host_raw(struct fosphor_cu *e, const void *raw_host,
 		const size_t samples = (size_t)((nc * batch - 1) * hop + n);
 		float2 *dev = nullptr;
 		int rc = upload_staged(e, raw + c0 * batch * hop, samples, &dev);
-		if (rc)
+		if (!rc)
+			rc = process_device_calls(e, dev, (int)nc, batch, hop);
+		if (!rc)
+			rc = release_slot(e);
+		if (rc) {
+			await_uploads(e);
 			return rc;
-		rc = process_device_calls(e, dev, (int)nc, batch, hop);
-		if (rc)
-			return rc;
-		rc = release_slot(e);
-		if (rc)
-			return rc;
+		}
 	}
-	return 0;
+	return await_uploads(e);              /* the whole raw buffer stays the caller's until here: copies run back to back */
 }
 
 int fosphor_cu_finish(struct fosphor_cu *e, float *waterfall_host,
