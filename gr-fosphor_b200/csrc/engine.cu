@@ -76,6 +76,8 @@ struct fosphor_cu {
 	int overlap_chunk = 16;              /* env FOSPHOR_B200_OVERLAP_CHUNK: calls per chunk of the two-stream schedule */
 	int acc_slim = 1;                    /* env FOSPHOR_B200_ACC_SLIM: two-stream mode uses the 14-warp fused kernel that
 	                                      * is co-resident with two FFT CTAs per SM */
+	int fft_r64 = 0;                     /* env FOSPHOR_B200_FFT_R64: two-pass radix-64 plans for N = 2048 / 4096 */
+	int plan_key = 0;                    /* fft_len, +1 for the radix-64 plan */
 	int fft_pf = -1;                     /* env FOSPHOR_B200_FFT_PF: L2 prefetch distance (spectra) of the plain FFT kernel;
 	                                      * -1 = the number of resident CTAs, 0 = off */
 	int fft_ctas_per_sm = 0;             /* env FOSPHOR_B200_FFT_CTAS: force the CTAs/SM of the persistent FFT
@@ -251,6 +253,8 @@ cudaError_t plan_launch(fosphor_cu *e, const float2 *in, long long hop, int wf_p
 	case 512:   { using P = Plan512;   EXPR; } break;      \
 	case 1024:  { using P = Plan1024;  EXPR; } break;      \
 	case 2048:  { using P = Plan2048;  EXPR; } break;      \
+	case 2049:  { using P = Plan2048R64; EXPR; } break;    \
+	case 4097:  { using P = Plan4096R64; EXPR; } break;    \
 	case 4096:  { using P = Plan4096;  EXPR; } break;      \
 	case 8192:  { using P = Plan8192;  EXPR; } break;      \
 	case 16384: { using P = Plan16384; EXPR; } break;      \
@@ -360,7 +364,7 @@ cudaError_t launch_fft(fosphor_cu *e, const float2 *in, long long hop, int wf_po
 		/* The CTA-level streaming kernel measured SLOWER than the plain one (N = 4096:
 		 * 101 vs 86 us per 8192 spectra; fewer resident CTAs outweigh the prefetch), so
 		 * it is only reachable as experiment variant 3. */
-		if (e->fft_variant == 3) {
+		if (e->fft_variant == 3 && e->plan_key == e->p.fft_len) {
 			if (e->p.fft_len == 2048)
 				return cta_stream_launch<Plan2048>(e, in, hop, wf_pos, n_spectra);
 			if (e->p.fft_len == 4096)
@@ -370,7 +374,7 @@ cudaError_t launch_fft(fosphor_cu *e, const float2 *in, long long hop, int wf_po
 		}
 	}
 	cudaError_t err = cudaErrorInvalidValue;
-	PLAN_SWITCH(e->p.fft_len, (err = plan_launch<P, false>(e, in, hop, wf_pos, nullptr, n_spectra)));
+	PLAN_SWITCH(e->plan_key, (err = plan_launch<P, false>(e, in, hop, wf_pos, nullptr, n_spectra)));
 	return err;
 }
 
@@ -967,11 +971,14 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 
 	{
 		std::vector<float2> tw;
-		PLAN_SWITCH(p.fft_len, build_twiddles<P>(tw));
+		if (const char *v = getenv("FOSPHOR_B200_FFT_R64"))
+			e->fft_r64 = atoi(v);
+		e->plan_key = p.fft_len + ((e->fft_r64 && (p.fft_len == 2048 || p.fft_len == 4096)) ? 1 : 0);
+		PLAN_SWITCH(e->plan_key, build_twiddles<P>(tw));
 		CREATE_CHECK(cudaMalloc(&e->d_tw, sizeof(float2) * tw.size()));
 		CREATE_CHECK(cudaMemcpy(e->d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
 		cudaError_t perr = cudaErrorInvalidValue;
-		PLAN_SWITCH(p.fft_len, (perr = plan_setup<P>()));
+		PLAN_SWITCH(e->plan_key, (perr = plan_setup<P>()));
 		CREATE_CHECK(perr);
 		if (p.fft_len == 1024)
 			CREATE_CHECK(stream_setup<Plan1024>());
@@ -1239,7 +1246,7 @@ int fosphor_cu_debug_fft(struct fosphor_cu *e, const void *samples_dev,
 	if (!e || !samples_dev || !out_dev || n_spectra < 0 || hop < 1)
 		return -EINVAL;
 	cudaError_t err = cudaErrorInvalidValue;
-	PLAN_SWITCH(e->p.fft_len, (err = plan_launch<P, true>(e, static_cast<const float2 *>(samples_dev), hop, 0,
+	PLAN_SWITCH(e->plan_key, (err = plan_launch<P, true>(e, static_cast<const float2 *>(samples_dev), hop, 0,
 	                                                      static_cast<float2 *>(out_dev), n_spectra)));
 	CU_CHECK(e, err);
 	return 0;

@@ -45,7 +45,7 @@ struct FftPlan {
 	 * wavefronts of N = 2048 / 8192 were conflict replays with a shift of 3) */
 	static constexpr int PADSHIFT = ilog2c(R0) < 4 ? 4 : ilog2c(R0);
 	/* launch bound of the plain kernel = the CTAs/SM that shared memory allows (8192: 3 CTAs at <= 80 registers) */
-	static constexpr int MIN_CTAS = N_ <= 1024 ? 4 : (N_ == 2048 ? 8 : (N_ == 4096 ? 4 : (N_ == 8192 ? 3 : 1)));
+	static constexpr int MIN_CTAS = R1_ == 64 ? 1 : (N_ <= 1024 ? 4 : (N_ == 2048 ? 8 : (N_ == 4096 ? 4 : (N_ == 8192 ? 3 : 1))));
 	static constexpr int SM_ELEMS = N + (N >> PADSHIFT);
 	static constexpr size_t SMEM = sizeof(float2) * (size_t)SM_ELEMS * SPB;
 	/* twiddle table: pass 1 [R1][P1] with P1 = R0, then pass 2 [R1][P2], P2 = R0*R1 */
@@ -663,5 +663,9 @@ using Plan2048  = FftPlan<2048,   8, 16, 3>;
 using Plan4096  = FftPlan<4096,  16, 16, 3>;
 using Plan8192  = FftPlan<8192,   8, 32, 3>;
 using Plan16384 = FftPlan<16384, 16, 32, 3>;
+/* two-pass alternatives with a radix-64 register pass: one shared-memory exchange and one twiddle
+ * stage less than the three-pass plans (those are LSU bound: 77-93 % l1tex in ncu) */
+using Plan2048R64 = FftPlan<2048, 32, 64, 2>;
+using Plan4096R64 = FftPlan<4096, 64, 64, 2>;
 
 } /* namespace fosphor_b200 */

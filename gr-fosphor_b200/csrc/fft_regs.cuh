@@ -1,5 +1,5 @@
 /*
- * fft_regs.cuh - in-register complex DFTs of size 2..32 for one thread.
+ * fft_regs.cuh - in-register complex DFTs of size 2..64 for one thread.
  *
  * Building block of the windowed-FFT kernel (fft_power.cuh) that replaces the
  * reference's fft1D_1024 OpenCL program (lib/fosphor/fft.cl:397-466; its
@@ -41,39 +41,47 @@ __host__ __device__ constexpr int brev(int k)
 	return r;
 }
 
-/* cos / sin of 2 pi q / 32, q = 0..8 (the rest by symmetry) */
-template <int Q> struct Cs32;
-template <> struct Cs32<0> { static constexpr float c = 1.0f, s = 0.0f; };
-template <> struct Cs32<1> { static constexpr float c = 0.98078528040323043f, s = 0.19509032201612825f; };
-template <> struct Cs32<2> { static constexpr float c = 0.92387953251128674f, s = 0.38268343236508978f; };
-template <> struct Cs32<3> { static constexpr float c = 0.83146961230254524f, s = 0.55557023301960218f; };
-template <> struct Cs32<4> { static constexpr float c = 0.70710678118654757f, s = 0.70710678118654757f; };
-template <> struct Cs32<5> { static constexpr float c = 0.55557023301960218f, s = 0.83146961230254524f; };
-template <> struct Cs32<6> { static constexpr float c = 0.38268343236508978f, s = 0.92387953251128674f; };
-template <> struct Cs32<7> { static constexpr float c = 0.19509032201612825f, s = 0.98078528040323043f; };
-template <> struct Cs32<8> { static constexpr float c = 0.0f, s = 1.0f; };
+/* cos / sin of 2 pi q / 64, q = 0..16 (the rest by symmetry) */
+template <int Q> struct Cs64;
+template <> struct Cs64<0>  { static constexpr float c = 1.0f, s = 0.0f; };
+template <> struct Cs64<1>  { static constexpr float c = 0.99518472667219693f, s = 0.098017140329560604f; };
+template <> struct Cs64<2>  { static constexpr float c = 0.98078528040323043f, s = 0.19509032201612825f; };
+template <> struct Cs64<3>  { static constexpr float c = 0.95694033573220882f, s = 0.29028467725446233f; };
+template <> struct Cs64<4>  { static constexpr float c = 0.92387953251128674f, s = 0.38268343236508978f; };
+template <> struct Cs64<5>  { static constexpr float c = 0.88192126434835505f, s = 0.47139673682599764f; };
+template <> struct Cs64<6>  { static constexpr float c = 0.83146961230254524f, s = 0.55557023301960218f; };
+template <> struct Cs64<7>  { static constexpr float c = 0.77301045336273699f, s = 0.63439328416364549f; };
+template <> struct Cs64<8>  { static constexpr float c = 0.70710678118654757f, s = 0.70710678118654757f; };
+template <> struct Cs64<9>  { static constexpr float c = 0.63439328416364549f, s = 0.77301045336273699f; };
+template <> struct Cs64<10> { static constexpr float c = 0.55557023301960218f, s = 0.83146961230254524f; };
+template <> struct Cs64<11> { static constexpr float c = 0.47139673682599764f, s = 0.88192126434835505f; };
+template <> struct Cs64<12> { static constexpr float c = 0.38268343236508978f, s = 0.92387953251128674f; };
+template <> struct Cs64<13> { static constexpr float c = 0.29028467725446233f, s = 0.95694033573220882f; };
+template <> struct Cs64<14> { static constexpr float c = 0.19509032201612825f, s = 0.98078528040323043f; };
+template <> struct Cs64<15> { static constexpr float c = 0.098017140329560604f, s = 0.99518472667219693f; };
+template <> struct Cs64<16> { static constexpr float c = 0.0f, s = 1.0f; };
 
-/* v *= exp(-2 pi i Q / 32), 0 <= Q < 16, with the trivial cases folded */
+/* v *= exp(-2 pi i Q / 64), 0 <= Q < 32, with the trivial cases folded */
 template <int Q>
-__device__ __forceinline__ float2 mul_w32(float2 v)
+__device__ __forceinline__ float2 mul_w64(float2 v)
 {
-	static_assert(Q >= 0 && Q < 16, "twiddle index");
+	static_assert(Q >= 0 && Q < 32, "twiddle index");
 	if constexpr (Q == 0) {
 		return v;
-	} else if constexpr (Q == 8) {            /* -i */
+	} else if constexpr (Q == 16) {           /* -i */
 		return make_float2(v.y, -v.x);
-	} else if constexpr (Q == 4) {            /* (1 - i) / sqrt2 */
-		constexpr float h = Cs32<4>::c;
+	} else if constexpr (Q == 8) {            /* (1 - i) / sqrt2 */
+		constexpr float h = Cs64<8>::c;
 		return make_float2((v.x + v.y) * h, (v.y - v.x) * h);
-	} else if constexpr (Q == 12) {           /* (-1 - i) / sqrt2 */
-		constexpr float h = Cs32<4>::c;
+	} else if constexpr (Q == 24) {           /* (-1 - i) / sqrt2 */
+		constexpr float h = Cs64<8>::c;
 		return make_float2((v.y - v.x) * h, -(v.x + v.y) * h);
-	} else if constexpr (Q < 8) {
-		constexpr float c = Cs32<Q>::c, s = Cs32<Q>::s;   /* w = c - i s */
+	} else if constexpr (Q < 16) {
+		constexpr float c = Cs64<Q>::c, s = Cs64<Q>::s;   /* w = c - i s */
 		return make_float2(fmaf(v.y, s, v.x * c), fmaf(-v.x, s, v.y * c));
 	} else {
-		/* Q in 9..15: w = -cos(pi - a) - i sin(pi - a), a = 2 pi Q / 32 */
-		constexpr float c = -Cs32<16 - Q>::c, s = Cs32<16 - Q>::s;
+		/* Q in 17..31: w = -cos(pi - a) - i sin(pi - a), a = 2 pi Q / 64 */
+		constexpr float c = -Cs64<32 - Q>::c, s = Cs64<32 - Q>::s;
 		return make_float2(fmaf(v.y, s, v.x * c), fmaf(-v.x, s, v.y * c));
 	}
 }
@@ -88,7 +96,7 @@ __device__ __forceinline__ void dif_level(float2 (&v)[R])
 			constexpr int j = decltype(jc)::value;
 			const float2 a = v[BASE + j], b = v[BASE + j + H];
 			v[BASE + j] = make_float2(a.x + b.x, a.y + b.y);
-			v[BASE + j + H] = mul_w32<j * (32 / M)>(make_float2(a.x - b.x, a.y - b.y));
+			v[BASE + j + H] = mul_w64<j * (64 / M)>(make_float2(a.x - b.x, a.y - b.y));
 		});
 		dif_level<H, BASE, R>(v);
 		dif_level<H, BASE + H, R>(v);
@@ -98,7 +106,7 @@ __device__ __forceinline__ void dif_level(float2 (&v)[R])
 template <int R>
 __device__ __forceinline__ void dif(float2 (&v)[R])
 {
-	static_assert(R >= 2 && R <= 32 && (R & (R - 1)) == 0, "radix");
+	static_assert(R >= 2 && R <= 64 && (R & (R - 1)) == 0, "radix");
 	dif_level<R, 0, R>(v);
 }
 

@@ -52,6 +52,22 @@ def test_fft_matches_double_dft(torch_cuda, n):
     eng.close()
 
 
+@pytest.mark.parametrize("n", [2048, 4096])
+def test_fft_radix64_plans_match_double_dft(torch_cuda, n, monkeypatch):
+    """two-pass plans with a radix-64 register pass (FOSPHOR_B200_FFT_R64=1): the transform
+    against the double DFT, and the whole path against the oracle."""
+    monkeypatch.setenv("FOSPHOR_B200_FFT_R64", "1")
+    test_fft_matches_double_dft(torch_cuda, n)
+    b = 64
+    x = signals.noise_tones(n * b, n_fft=n, seed=60 + n, sigma=0.02)
+    eng, host, orc = _run_both(torch_cuda, dict(fft_len=n, n_bins=256, wf_rows=1024), [x])
+    rows_written = np.arange(b)
+    parity.check_waterfall(host["waterfall"], orc.waterfall, rows=rows_written)
+    parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=b * n)
+    parity.check_spectrum(host["spectrum"], orc.spectrum, wf_ref=orc.waterfall[rows_written])
+    eng.close()
+
+
 def test_fft_hop_addressing(torch_cuda):
     """hop < N reads overlapping windows from the raw stream (overlap_cc_impl.cc:64-79)."""
     torch = torch_cuda
