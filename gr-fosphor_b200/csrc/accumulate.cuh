@@ -1,6 +1,13 @@
 /*
- * accumulate.cuh - kernels 2a/2b of the hot path: fold the log-power rows of
- * one or more calls into the persistence state.
+ * accumulate.cuh - kernel 2 of the hot path: fold the log-power rows of one or
+ * more calls into the persistence state.
+ *
+ * Two implementations of the same arithmetic:
+ *   accumulate_fused_kernel (second half of this file) - the default: ONE launch,
+ *      state tile resident in shared memory, warp-specialised counters / updaters;
+ *   count_kernel / count_tma_kernel + update_kernel (first half) - the any-shape
+ *      fallback (batches that are not multiples of 16 rows, 2B < K), hit counts
+ *      through HBM as u16.
  *
  * Replaces the second half of the reference's display program:
  *   lib/fosphor/display.cl:149-150,186-214  live spectrum (weighted IIR)
@@ -9,7 +16,8 @@
  *   lib/fosphor/display.cl:257-310          max hold with decay
  * The reference runs all of this on a fixed 64 work-groups that each loop over
  * the whole batch and then over all bins (cl.c:945-948).  Here the work is cut
- * along its real dependencies:
+ * along its real dependencies (described for the split kernels; the fused
+ * kernel keeps the same cut inside one CTA):
  *
  *  count_kernel  (embarrassingly parallel over tiles x slices)
  *      A slice is a run of rows of ONE call; a tile is 32 columns.  Each CTA

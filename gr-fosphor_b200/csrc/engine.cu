@@ -32,9 +32,9 @@ enum { ST_BOOTING = 0, ST_PENDING, ST_READY };   /* cl.c:95-99 */
 
 constexpr int N_TABLES = 8;      /* cached (weights, lut) sets, one per distinct batch size */
 constexpr int MAX_SLICES = 128;  /* (call, row-split) slices folded by one count/update launch pair */
-constexpr size_t CNT_BUDGET = (size_t)1 << 30;
+constexpr size_t CNT_BUDGET = (size_t)1 << 30;   /* bytes of u16 hit-count slices kept on the device (split kernels) */
 constexpr int N_CHUNK_EV = 64;   /* chunks in flight tracked by the two-stream schedule */
-constexpr size_t UPD_SMEM_MAX = 96 * 1024;   /* dynamic shared memory of update_kernel */   /* bytes of u16 hit-count slices kept on the device */
+constexpr size_t UPD_SMEM_MAX = 96 * 1024;   /* dynamic shared memory of update_kernel */
 
 struct BatchTables {
 	int batch = -1;
@@ -352,9 +352,6 @@ cudaError_t launch_fft(fosphor_cu *e, const float2 *in, long long hop, int wf_po
 	/* TMA bulk copies need 16-byte aligned spectra */
 	const bool aligned = ((reinterpret_cast<unsigned long long>(in) & 15ull) == 0) && ((hop & 1) == 0);
 	if (aligned && e->fft_variant != 0) {
-		if (e->p.fft_len == 1024 || e->p.fft_len == 512) {
-			/* variant 3 means "2 + experiments" for these sizes */
-		}
 		if (e->p.fft_len == 1024)
 			return stream_launch<Plan1024>(e, in, hop, wf_pos, n_spectra);
 		if (e->p.fft_len == 512)
