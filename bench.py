@@ -37,7 +37,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 N_FFT, N_BINS, OVERLAP, BATCH, CALLS_PER_STEP = 1024, 256, 4, 1024, 384
-WF_ROWS = 65536  # device waterfall ring: one FFT + one accumulate launch per 64 calls (per-launch ramp/tail ~8 us)
+WF_ROWS = 262144  # device waterfall ring (1 GiB): 256 calls; the engine's two-stream schedule then works in chunks of 64 calls
 REF_CALLS_PER_STEP = 8   # reference arm: one sink frame (base_sink_c_impl.cc:133-146) per step
 
 
@@ -184,20 +184,24 @@ def run_b200(args):
 
     wf_rows = args.wf_rows
 
-    def make_engine(rows, overlap):
-        """overlap False: every kernel on one stream (clean per-kernel timing);
-        True: count/update of one chunk beside the FFT of the next (needs 2 chunks of ring)."""
+    def make_engine(rows, mode):
+        """mode None: the engine's default schedule (automatic: two streams when the ring holds four
+        chunks of >= 32 M samples); "0": every kernel on one stream (kernels timed
+        alone, clean per-kernel event timing)."""
         old = os.environ.get("FOSPHOR_B200_OVERLAP")
-        os.environ["FOSPHOR_B200_OVERLAP"] = "1" if overlap else "0"
+        if mode is None:
+            os.environ.pop("FOSPHOR_B200_OVERLAP", None)
+        else:
+            os.environ["FOSPHOR_B200_OVERLAP"] = mode
         try:
             return Fosphor(fft_len=n, n_bins=k, wf_rows=rows, device=local, stream=stream.cuda_stream)
         finally:
             if old is None:
-                os.environ.pop("FOSPHOR_B200_OVERLAP")
+                os.environ.pop("FOSPHOR_B200_OVERLAP", None)
             else:
                 os.environ["FOSPHOR_B200_OVERLAP"] = old
 
-    eng = make_engine(wf_rows, False)
+    eng = make_engine(wf_rows, None)
 
     # ---- inputs: two distinct seconds of signal, raw and pre-overlapped (3.2 GB each >> L2) ----
     pool_n = raw_pool_n = 2
@@ -251,44 +255,51 @@ def run_b200(args):
     launches_timed = launches * args.steps // (args.steps + args.warmup)
     value = world * args.steps * samples_per_step / (ms * 1e-3) / 1e6
 
-    # per-kernel durations: same loop again with event pairs around each launch
+    # per-kernel durations while co-running (default schedule): event pairs around each launch
     eng.profile(True)
     prof_steps = min(args.steps, 5)
     timed(lambda i: step_device(i, True), prof_steps, 0)
+    prof_co = eng.profile_read()
+    eng.profile(False)
+    step_bytes = calls * algorithmic_bytes_per_call(n, k, b, 1.0)
+
+    # ---- the same workload with every kernel on one stream: kernels timed ALONE ----
+    eng_default = eng
+    eng = make_engine(wf_rows, "0")
+    ms_one = timed(lambda i: step_device(i, True), args.steps, args.warmup)
+    eng.profile(True)
+    timed(lambda i: step_device(i, True), prof_steps, 0)
     prof = eng.profile_read()
     eng.profile(False)
+    eng.close()
+    eng = eng_default
     fft_ms = prof["fft_ms"] / max(1, prof["fft_launches"])
     count_ms = prof["count_ms"] / max(1, prof["count_launches"])
     update_ms = prof["update_ms"] / max(1, prof["update_launches"])
     spectra_per_fft_launch = spectra_per_step * prof_steps // max(1, prof["fft_launches"])
     fft_bytes = fft_kernel_bytes(n, spectra_per_fft_launch, 1.0)
     achieved = fft_bytes / (fft_ms * 1e-3) / 1e9
-    step_bytes = calls * algorithmic_bytes_per_call(n, k, b, 1.0)
+    spectra_per_fft_launch_co = spectra_per_step * prof_steps // max(1, prof_co["fft_launches"])
+    fft_ms_co = prof_co["fft_ms"] / max(1, prof_co["fft_launches"])
+    acc_ms_co = (prof_co["count_ms"] / max(1, prof_co["count_launches"]) +
+                 prof_co["update_ms"] / max(1, prof_co["update_launches"]))
 
     traffic = None
+    acc_traffic_per_call = None
     tpath = os.path.join(ROOT, "profiles", "fft_power_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-
-    # ---- two-stream mode: accumulate of chunk c beside the FFT of chunk c+1 (same ring, two chunks) ----
-    eng_one = eng
-    eng = make_engine(wf_rows, True)
-    ms_two = timed(lambda i: step_device(i, True), args.steps, args.warmup)
-    eng.profile(True)
-    timed(lambda i: step_device(i, True), prof_steps, 0)
-    prof_two = eng.profile_read()
-    eng.profile(False)
-    two = {"value": world * args.steps * samples_per_step / (ms_two * 1e-3) / 1e6,
-           "unit": "Mcomplex-samples/s", "ms_per_step": ms_two / args.steps, "wf_rows": wf_rows,
-           "step_frac": step_bytes / (ms_two / args.steps * 1e-3) / 1e9 / peak,
-           "fft_ms_per_launch_concurrent": prof_two["fft_ms"] / max(1, prof_two["fft_launches"]),
-           "accumulate_ms_per_launch_concurrent": prof_two["count_ms"] / max(1, prof_two["count_launches"]) +
-           prof_two["update_ms"] / max(1, prof_two["update_launches"]),
-           "note": "FOSPHOR_B200_OVERLAP=1 (not the default): accumulate kernel of one half-ring chunk on a second "
-                   "stream beside the FFT of the next; both slow down in proportion, see DESIGN.md"}
-    eng.close()
-    eng = eng_one
+            tj = json.load(f)
+        # ncu capture was taken at 65536 spectra per launch: scale to this run's launch size
+        traffic = tj.get("dram_bytes_per_launch") * spectra_per_fft_launch / tj.get("spectra_per_launch", 65536)
+        acc_traffic_per_call = tj.get("accumulate_dram_bytes_per_call")
+    one = {"value": world * args.steps * samples_per_step / (ms_one * 1e-3) / 1e6,
+           "unit": "Mcomplex-samples/s", "ms_per_step": ms_one / args.steps,
+           "step_frac": step_bytes / (ms_one / args.steps * 1e-3) / 1e9 / peak,
+           "fft_share_of_kernel_time": fft_ms * prof["fft_launches"] /
+           max(1e-9, prof["fft_ms"] + prof["count_ms"] + prof["update_ms"]),
+           "note": "FOSPHOR_B200_OVERLAP=0: FFT and accumulate launches back to back on one stream; the per-kernel "
+                   "numbers of `roofline` come from this pass (kernels timed alone)"}
 
     # ---- in-engine overlap variant (raw stream, hop = N/4) ----
     ms_hop = timed(lambda i: step_device(i, False), args.steps, args.warmup)
@@ -346,7 +357,7 @@ def run_b200(args):
     del pool, raws
     torch.cuda.empty_cache()
     eng_dev = eng
-    eng = make_engine(1024, False)   # reference-sized ring
+    eng = make_engine(1024, None)    # reference-sized ring
     ms_e2e = timed_host(step_e2e, e2e_steps, 1)
     e2e = world * e2e_steps * samples_per_step / (ms_e2e * 1e-3) / 1e6
     ms_e2e_raw = timed_host(step_e2e_raw, e2e_steps, 1)
@@ -370,6 +381,7 @@ def run_b200(args):
                                    "spectra/call, step = 1 s of 100 Msps IQ = 384 calls = 393216 spectra",
                        "fft_len": n, "n_bins": k, "overlap": OVERLAP, "batch": b, "calls_per_step": calls,
                        "wf_rows": wf_rows,
+                       "schedule": "engine default (automatic): two streams, chunks of wf_rows/4 rows",
                        "l2": "each step streams a %d MiB input (two alternating buffers), far larger than the 126 MB L2" % (samples_per_step * 8 // 2**20),
                        "multi_gpu": "one channel per GPU, NCCL max all-reduce of max-hold per step" if world > 1 else "single"},
             "gpu_launches": int(launches_timed),
@@ -377,16 +389,26 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": "fft_power_stream_kernel<Plan1024, TWREG>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic,
+                         "timed": "kernel alone: CUDA events around each launch in the one-stream pass of the same "
+                                  "workload (`one_stream`); in the default schedule it shares HBM with the "
+                                  "accumulate kernel of the previous chunk, see `concurrent`",
                          "bytes_per_launch": fft_bytes, "ms_per_launch": fft_ms,
                          "spectra_per_launch": spectra_per_fft_launch,
                          "accumulate_kernel": "accumulate_fused_kernel<COLS=8, 16 counter + 8 updater warps, 256-row TMA boxes> (count + rise/decay + live + max-hold, one launch)",
                          "accumulate_ms_per_launch": count_ms + update_ms,
+                         "concurrent": {"schedule": "FFT of chunk c+1 beside the accumulate kernel of chunk c (two streams)",
+                                        "spectra_per_launch": spectra_per_fft_launch_co,
+                                        "fft_ms_per_launch": fft_ms_co, "accumulate_ms_per_launch": acc_ms_co,
+                                        "fft_achieved_GBps": fft_kernel_bytes(n, spectra_per_fft_launch_co, 1.0) / (fft_ms_co * 1e-3) / 1e9,
+                                        "step_dram_GBps": None if traffic is None or acc_traffic_per_call is None else
+                                        (traffic / spectra_per_fft_launch * spectra_per_step + acc_traffic_per_call * calls) /
+                                        (ms / args.steps * 1e-3) / 1e9},
                          "step_algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                          "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e, "unit": "Mcomplex-samples/s",
                     "h2d_bytes_per_step": 8 * samples_per_step, "d2h_bytes_per_step": d2h,
                     "api": "fosphor_cu_process_host x384 + fosphor_cu_finish (page-locked host pre-overlapped stream)"},
-            "two_stream_overlap": two,
+            "one_stream": one,
             "overlap_in_engine": {"value": value_hop, "e2e": e2e_raw, "unit": "Mcomplex-samples/s",
                                   "h2d_bytes_per_step": 8 * raw_len,
                                   "note": "raw stream, hop=N/4 addressing inside the FFT kernel (r=1/4)"},

@@ -63,16 +63,22 @@ struct fosphor_cu {
 	cudaEvent_t cnt_done[N_CHUNK_EV] = {};
 	cudaEvent_t acc_done = nullptr;
 	cudaEvent_t cols_fork = nullptr, cols_join = nullptr;   /* column update runs beside the cell update */
-	int overlap = 0;                     /* env FOSPHOR_B200_OVERLAP: 1 = the accumulate kernels of chunk c run on a
-	                                      * second stream while the FFT of chunk c+1 runs (needs a ring of >= 2
-	                                      * chunks; the persistent FFT kernel then takes 2 CTAs per SM).  Default 0 =
-	                                      * one stream: measured with a 64-call ring, co-running buys nothing (old
-	                                      * split kernels 310 vs 306 Gsamples/s) or loses (fused kernel 283 vs 315):
-	                                      * both kernels slow down in proportion - the accumulate kernel re-reads the
-	                                      * waterfall chunk from HBM (134 MB per 32 calls, ncu) and competes for
-	                                      * the same issue slots - while halving the chunk doubles the launch
-	                                      * ramp/tail cost (~8 us per launch). */
+	int overlap = -1;                    /* env FOSPHOR_B200_OVERLAP.  Two-stream schedule: the accumulate kernel of chunk c
+	                                      * runs on a second (higher priority) stream while the FFT of chunk c+1 runs.
+	                                      * -1 (default) = automatic: on when the ring holds four chunks of >= 32 M samples
+	                                      *    (N = 512 / 1024 streaming FFT + fused accumulate); chunk = ring / 4, full-size
+	                                      *    accumulate CTAs, FFT at 3 CTAs/SM.  The accumulate CTAs take 128 SMs, the next
+	                                      *    FFT starts on the 20 that are left and on every SM an accumulate CTA leaves:
+	                                      *    cfg2, 256-call ring: 385 vs 345 Gsamples/s; DRAM traffic at 0.91 of the peak.
+	                                      *    Smaller rings lose: chunks of 16 calls pay the launch ramp/tail 4x as often
+	                                      *    (64-call ring: 327 vs 345).
+	                                      *  0 = one stream.   1 = forced, with OVERLAP_CHUNK / ACC_SLIM / FFT_CTAS knobs. */
 	bool two_streams_now = false;        /* set per process call */
+	bool acc_pending = false;            /* accumulate work on acc_stream that `stream` has not been ordered after yet */
+	long long chunk_seq = 0;             /* chunks issued by the two-stream schedule since the last join */
+	unsigned long long two_stream_chunks = 0;   /* ... since create (diagnostics) */
+	int seq_batch = 0, seq_chunk_calls = 0;   /* ... and their geometry (a change forces a join) */
+	bool slim_now = false;               /* ... two-stream mode with the slim co-resident accumulate CTA */
 	int overlap_chunk = 16;              /* env FOSPHOR_B200_OVERLAP_CHUNK: calls per chunk of the two-stream schedule */
 	int acc_slim = 1;                    /* env FOSPHOR_B200_ACC_SLIM: two-stream mode uses the 14-warp fused kernel that
 	                                      * is co-resident with two FFT CTAs per SM */
@@ -286,7 +292,7 @@ cudaError_t stream_launch(fosphor_cu *e, const float2 *in, long long hop, int wf
 	int per_sm = C::CTAS_PER_SM;
 	if (e->fft_ctas_per_sm > 0 && e->fft_ctas_per_sm < per_sm)
 		per_sm = e->fft_ctas_per_sm;
-	else if (e->fft_ctas_per_sm == 0 && e->two_streams_now && per_sm > 2)
+	else if (e->fft_ctas_per_sm == 0 && e->slim_now && per_sm > 2)
 		per_sm = 2;                      /* leave room for the count kernel on the other stream */
 	const int resident = e->sm_count * per_sm;
 	if (grid > resident)
@@ -552,7 +558,7 @@ int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st
 	}
 	prof_mark(e, 1, 0, st);
 	cudaError_t err;
-	const bool slim = e->two_streams_now && e->acc_slim;
+	const bool slim = e->slim_now;
 	if (slim)
 		subr = 16;      /* 46 registers (the 64-row body needs 56): 14 warps fit beside two FFT CTAs */
 	/* calls per synchronisation group: with few rows per call the barrier round trips between
@@ -593,13 +599,20 @@ int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st
 	return 0;
 }
 
+/* path choice depends on (B, K) only, never on the ring position or the launch
+ * folding: the two paths add the live spectrum in different orders */
+bool use_fused(const fosphor_cu *e, int batch)
+{
+	return e->acc_mode > 0 || (e->acc_mode < 0 && 2 * batch >= e->p.n_bins && (batch % 16) == 0 && e->acc_tmap_ok);
+}
+
 /* fold n_calls calls (rows wf_pos .. wf_pos + n_calls*batch of the ring) into the state */
 int launch_accumulate(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cudaEvent_t count_done,
                       int wf_pos, int n_calls, int batch)
 {
 	/* path choice depends on (B, K) only, never on the ring position or the launch
 	 * folding: the two paths add the live spectrum in different orders */
-	if (e->acc_mode > 0 || (e->acc_mode < 0 && 2 * batch >= e->p.n_bins && (batch % 16) == 0 && e->acc_tmap_ok))
+	if (use_fused(e, batch))
 		return launch_accumulate_fused(e, t, st, count_done, wf_pos, n_calls, batch);
 	AccumArgs a;
 	a.wf = e->d_wf;
@@ -654,6 +667,19 @@ int launch_accumulate(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cuda
 	return 0;
 }
 
+/* Two-stream schedule: order `stream` after everything issued on acc_stream.  Process calls do not
+ * do this on return - the FFT of the next call may start while the last accumulate launch of this
+ * one still runs - so every other consumer of the state on `stream` does it first. */
+int join_accumulate(fosphor_cu *e)
+{
+	if (e->acc_pending) {
+		CU_CHECK(e, cudaStreamWaitEvent(e->stream, e->acc_done, 0));
+		e->acc_pending = false;
+		e->chunk_seq = 0;
+	}
+	return 0;
+}
+
 int clear_buffers(fosphor_cu *e)
 {
 	/* cl.c:406-465: spectrum (all 4N floats) and waterfall = -power.offset
@@ -697,10 +723,20 @@ int process_device_calls(fosphor_cu *e, const float2 *in, int n_calls, int batch
 		 * chunk c+1 (main stream). */
 		const int ring_calls = e->p.wf_rows / batch;         /* >= 1: wf_rows >= batch_max */
 		int calls_per_chunk = ring_calls;
-		const bool want = e->overlap > 0;
-		int ov_chunk = e->overlap_chunk < ring_calls / 2 ? e->overlap_chunk : ring_calls / 2;
-		if (ov_chunk < 1) ov_chunk = 1;
-		const bool two_streams = want && ring_calls >= 2 && n_calls >= 2 * ov_chunk;
+		int ov_chunk = 1;
+		bool two_streams = false;
+		e->slim_now = false;
+		if (e->overlap > 0) {                        /* forced, knobs from the environment */
+			ov_chunk = e->overlap_chunk < ring_calls / 2 ? e->overlap_chunk : ring_calls / 2;
+			if (ov_chunk < 1) ov_chunk = 1;
+			two_streams = ring_calls >= 2 && n_calls >= 2 * ov_chunk;
+			e->slim_now = two_streams && e->acc_slim;
+		} else if (e->overlap < 0) {                 /* automatic, see the comment at `overlap` */
+			const bool stream_fft = (e->p.fft_len == 512 || e->p.fft_len == 1024) && e->fft_variant >= 2;
+			ov_chunk = ring_calls / 4;
+			two_streams = stream_fft && use_fused(e, batch) && ov_chunk >= 1 && ov_chunk <= e->max_slices &&
+			              (long long)ov_chunk * batch * e->p.fft_len >= (32ll << 20) && n_calls >= 2 * ov_chunk;
+		}
 		if (two_streams)
 			calls_per_chunk = ov_chunk;
 		e->two_streams_now = two_streams;
@@ -709,17 +745,27 @@ int process_device_calls(fosphor_cu *e, const float2 *in, int n_calls, int batch
 		if (e->chunk_calls > 0 && calls_per_chunk > e->chunk_calls)
 			calls_per_chunk = e->chunk_calls;
 		cudaStream_t acc = two_streams ? e->acc_stream : e->stream;
-		/* The FFT of chunk c overwrites ring rows last read by the accumulate launch of a
-		 * chunk no younger than c - lag (every chunk has at most calls_per_chunk calls):
-		 * waiting for that one - the acc stream is in order - frees them. */
+		/* a one-stream call, or another chunk geometry, first waits for what is still on acc_stream */
+		if (e->acc_pending && (!two_streams || e->seq_batch != batch || e->seq_chunk_calls != calls_per_chunk)) {
+			rc = join_accumulate(e);
+			if (rc)
+				return rc;
+		}
+		e->seq_batch = batch;
+		e->seq_chunk_calls = calls_per_chunk;
+		/* The FFT of chunk q overwrites ring rows last read by the accumulate launch of a
+		 * chunk no younger than q - lag (every chunk has at most calls_per_chunk calls):
+		 * waiting for that one - the acc stream is in order - frees them.  The chunk
+		 * sequence runs on across process calls until something joins the streams. */
 		int lag = ring_calls / calls_per_chunk;
 		if (lag > N_CHUNK_EV) lag = N_CHUNK_EV;
-		int chunk = 0;
-		for (int c0 = 0; c0 < n_calls; c0 += calls_per_chunk, chunk++) {
+		for (int c0 = 0; c0 < n_calls; c0 += calls_per_chunk) {
 			const int nc = n_calls - c0 < calls_per_chunk ? n_calls - c0 : calls_per_chunk;
-			const int pp = chunk % N_CHUNK_EV;
-			if (two_streams && chunk >= lag)
-				CU_CHECK(e, cudaStreamWaitEvent(e->stream, e->cnt_done[(chunk - lag) % N_CHUNK_EV], 0));
+			const long long q = two_streams ? e->chunk_seq++ : 0;
+			e->two_stream_chunks += two_streams ? 1 : 0;
+			const int pp = (int)(q % N_CHUNK_EV);
+			if (two_streams && q >= lag)
+				CU_CHECK(e, cudaStreamWaitEvent(e->stream, e->cnt_done[(q - lag) % N_CHUNK_EV], 0));
 			CU_CHECK(e, launch_fft(e, in + (long long)c0 * batch * hop, hop, e->wf_pos, nc * batch));
 			if (two_streams) {
 				CU_CHECK(e, cudaEventRecord(e->fft_done[pp], e->stream));
@@ -730,9 +776,9 @@ int process_device_calls(fosphor_cu *e, const float2 *in, int n_calls, int batch
 				return rc;
 			e->wf_pos = (e->wf_pos + nc * batch) & (e->p.wf_rows - 1);   /* cl.c:954, nc times */
 		}
-		if (two_streams) {                       /* join: the caller's stream sees the finished state */
+		if (two_streams) {                       /* what a later join waits for */
 			CU_CHECK(e, cudaEventRecord(e->acc_done, acc));
-			CU_CHECK(e, cudaStreamWaitEvent(e->stream, e->acc_done, 0));
+			e->acc_pending = true;
 		}
 	}
 	e->state = ST_PENDING;                /* cl.c:957 */
@@ -912,7 +958,14 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 	e->smem_optin = prop.sharedMemPerBlockOptin;
 	CREATE_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
 	e->stream = e->own_stream;
-	CREATE_CHECK(cudaStreamCreateWithFlags(&e->acc_stream, cudaStreamNonBlocking));
+	{
+		/* the accumulate stream outranks the FFT stream: in the two-stream schedule the accumulate CTAs
+		 * of chunk c (one per SM, most of its shared memory) must get their SMs before the FFT CTAs of
+		 * chunk c+1 refill them */
+		int prio_lo = 0, prio_hi = 0;
+		CREATE_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		CREATE_CHECK(cudaStreamCreateWithPriority(&e->acc_stream, cudaStreamNonBlocking, prio_hi));
+	}
 	for (int i = 0; i < N_CHUNK_EV; i++) {
 		CREATE_CHECK(cudaEventCreateWithFlags(&e->fft_done[i], cudaEventDisableTiming));
 		CREATE_CHECK(cudaEventCreateWithFlags(&e->cnt_done[i], cudaEventDisableTiming));
@@ -1081,6 +1134,8 @@ int fosphor_cu_set_stream(struct fosphor_cu *e, void *cuda_stream)
 {
 	if (!e)
 		return -EINVAL;
+	if (int rc = join_accumulate(e))
+		return rc;
 	CU_CHECK(e, cudaStreamSynchronize(e->stream));
 	e->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->own_stream;
 	return 0;
@@ -1190,6 +1245,8 @@ int fosphor_cu_finish(struct fosphor_cu *e, float *waterfall_host,
 		if (rc)
 			return rc;
 	}
+	if (int rc = join_accumulate(e))
+		return rc;
 	const size_t n = e->p.fft_len;
 	/* cl.c:1012-1048 */
 	if (waterfall_host)
@@ -1210,8 +1267,22 @@ int fosphor_cu_sync(struct fosphor_cu *e)
 {
 	if (!e)
 		return -EINVAL;
+	if (int rc = join_accumulate(e))
+		return rc;
 	CU_CHECK(e, cudaStreamSynchronize(e->stream));
 	return 0;
+}
+
+unsigned long long fosphor_cu_two_stream_chunks(const struct fosphor_cu *e)
+{
+	return e ? e->two_stream_chunks : 0;
+}
+
+int fosphor_cu_flush(struct fosphor_cu *e)
+{
+	if (!e)
+		return -EINVAL;
+	return join_accumulate(e);
 }
 
 int fosphor_cu_get_waterfall_position(const struct fosphor_cu *e)
@@ -1231,6 +1302,8 @@ int fosphor_cu_export_maxhold(struct fosphor_cu *e, float *out_dev)
 	if (!e || !out_dev)
 		return -EINVAL;
 	const int n = e->p.fft_len;
+	if (int rc = join_accumulate(e))
+		return rc;
 	export_maxhold_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_spec, n, out_dev);
 	e->launches++;
 	CU_CHECK(e, cudaGetLastError());
@@ -1253,6 +1326,8 @@ int fosphor_cu_profile(struct fosphor_cu *e, int enable)
 {
 	if (!e)
 		return -EINVAL;
+	if (int rc = join_accumulate(e))
+		return rc;
 	CU_CHECK(e, cudaStreamSynchronize(e->stream));
 	e->profiling = enable != 0;
 	e->prof_used[0] = e->prof_used[1] = e->prof_used[2] = 0;
@@ -1263,6 +1338,8 @@ int fosphor_cu_profile_read(struct fosphor_cu *e, double *ms_out, unsigned long 
 {
 	if (!e)
 		return -EINVAL;
+	if (int rc = join_accumulate(e))
+		return rc;
 	CU_CHECK(e, cudaStreamSynchronize(e->stream));
 	double ms[3] = {0.0, 0.0, 0.0};
 	for (int k = 0; k < 3; k++)

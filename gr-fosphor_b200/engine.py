@@ -48,6 +48,9 @@ def load_library(path=None):
     L.fosphor_cu_process_host_raw.argtypes = [vp, vp, C.c_int, C.c_int, ll]
     L.fosphor_cu_finish.argtypes = [vp, vp, vp, vp]
     L.fosphor_cu_sync.argtypes = [vp]
+    L.fosphor_cu_flush.argtypes = [vp]
+    L.fosphor_cu_two_stream_chunks.argtypes = [vp]
+    L.fosphor_cu_two_stream_chunks.restype = C.c_ulonglong
     L.fosphor_cu_get_waterfall_position.argtypes = [vp]
     for n in ("waterfall", "histogram", "spectrum"):
         f = getattr(L, "fosphor_cu_device_" + n)
@@ -169,6 +172,14 @@ class Fosphor:
 
     def sync(self):
         return self._chk(self.lib.fosphor_cu_sync(self.h))
+
+    @property
+    def two_stream_chunks(self):
+        return int(self.lib.fosphor_cu_two_stream_chunks(self.h))
+
+    def flush(self):
+        """order the engine's stream after all process work enqueued so far (no host wait)"""
+        return self._chk(self.lib.fosphor_cu_flush(self.h))
 
     @property
     def waterfall_position(self):

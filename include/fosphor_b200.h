@@ -127,10 +127,19 @@ int fosphor_cu_finish(struct fosphor_cu *e, float *waterfall_host,
                       float *histogram_host, float *spectrum_host);
 /* Wait for all enqueued work (no copies). */
 int fosphor_cu_sync(struct fosphor_cu *e);
+/* Order the engine's stream after all process work enqueued so far, without waiting on the host.
+ * Large device-resident batches run their accumulate kernels on a second internal stream and a
+ * process call does NOT join it on return (the next call's FFT may start while the last accumulate
+ * launch still runs).  finish / sync / export_maxhold / set_stream join by themselves; callers
+ * that read the device arrays below from their own work on the engine's stream call this first. */
+int fosphor_cu_flush(struct fosphor_cu *e);
+/* Diagnostics: chunks that went through the two-stream schedule since create. */
+unsigned long long fosphor_cu_two_stream_chunks(const struct fosphor_cu *e);
 
 int fosphor_cu_get_waterfall_position(const struct fosphor_cu *e);
 
-/* "Plain device arrays" (BASELINE.json north_star): valid until destroy. */
+/* "Plain device arrays" (BASELINE.json north_star): valid until destroy; contents are
+ * stream ordered after fosphor_cu_flush(). */
 float *fosphor_cu_device_waterfall(struct fosphor_cu *e);  /* [wf_rows][N]      */
 float *fosphor_cu_device_histogram(struct fosphor_cu *e);  /* [n_bins][N]       */
 float *fosphor_cu_device_spectrum(struct fosphor_cu *e);   /* [2][N][2]         */

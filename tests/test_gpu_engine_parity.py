@@ -397,6 +397,32 @@ def test_small_batches_folded_launches_vs_oracle(torch_cuda, b):
         e.close()
 
 
+def test_automatic_two_stream_schedule_is_bit_identical(torch_cuda, monkeypatch):
+    """A ring of four chunks of >= 32 M samples switches the engine to its two-stream schedule
+    (accumulate of chunk c beside the FFT of chunk c+1, streams joined lazily: three process calls
+    in a row without a finish).  Results must equal the one-stream schedule bit for bit."""
+    torch = torch_cuda
+    n, k, b, calls, hop, rows = 1024, 256, 1024, 96, 256, 131072
+    raw = signals.noise_tones((calls * b - 1) * hop + n, seed=404)
+    d_raw = _to_dev(torch, raw)
+    outs = []
+    for mode in (None, "0"):
+        if mode is None:
+            monkeypatch.delenv("FOSPHOR_B200_OVERLAP", raising=False)
+        else:
+            monkeypatch.setenv("FOSPHOR_B200_OVERLAP", mode)
+        e = _engine(n_bins=k, wf_rows=rows)
+        for rep in range(3):                      # the ring wraps; no join between the calls
+            assert e.process_device_multi(d_raw.data_ptr(), calls, b, hop) == 0
+        assert (e.two_stream_chunks > 0) == (mode is None)
+        _, h = e.finish()
+        outs.append({key: v.copy() for key, v in h.items()})
+        assert e.waterfall_position == (3 * calls * b) % rows
+        e.close()
+    for key in ("waterfall", "histogram", "spectrum"):
+        assert np.array_equal(outs[0][key], outs[1][key]), key
+
+
 def test_histogram_mass_property(torch_cuda):
     """From a zero histogram one call deposits, per column, exactly the mass the
     closed form predicts from hit counts summing to B: sum_bins d(hc)*(1-e(hc)).

@@ -24,6 +24,9 @@ def main():
               "n8192": ("n8192", 8192, 256, 4, 1024, 32, 16384, True, {}),
               "n16384": ("n16384", 16384, 256, 4, 1024, 32, 16384, True, {}),
               "cfg2r64": ("cfg2r64", 1024, 256, 4, 1024, 128, 65536, False, {}),
+              "cfg2r128": ("cfg2r128", 1024, 256, 4, 1024, 256, 131072, False, {}),
+              "cfg2r256": ("cfg2r256", 1024, 256, 4, 1024, 512, 262144, False, {}),
+              "cfg2r512": ("cfg2r512", 1024, 256, 4, 1024, 1024, 524288, False, {}),
               "n512": ("n512", 512, 256, 4, 1024, 128, 65536, True, {})}
     which = sys.argv[1:] or ["cfg2"]
     variants = [
@@ -48,7 +51,7 @@ def main():
         for var in variants:
             for key, v in var.items():
                 os.environ["FOSPHOR_B200_" + key] = v
-            for mode in modes:
+            for mode in ((var["OVERLAP"],) if "OVERLAP" in var else modes):
                 os.environ["FOSPHOR_B200_OVERLAP"] = mode
                 r = perf_configs.run_one(torch, name, n, k, ov, b, calls, rows, ieo, **kw)
                 print(json.dumps({"shape": w, "variant": var, "two_stream": mode == "1",
