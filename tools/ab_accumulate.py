@@ -26,6 +26,12 @@ def main():
               "cfg2r64": ("cfg2r64", 1024, 256, 4, 1024, 128, 65536, False, {}),
               "cfg2r128": ("cfg2r128", 1024, 256, 4, 1024, 256, 131072, False, {}),
               "cfg2r256": ("cfg2r256", 1024, 256, 4, 1024, 512, 262144, False, {}),
+              "n4096r64": ("n4096r64", 4096, 256, 4, 1024, 128, 65536, True, {}),
+              "n2048r128": ("n2048r128", 2048, 256, 4, 1024, 256, 131072, True, {}),
+              "n16384r16": ("n16384r16", 16384, 256, 4, 1024, 32, 16384, True, {}),
+              "cfg3r256": ("cfg3r256", 4096, 512, 8, 256, 512, 65536, True, {"t0d": 20.0}),
+              "cfg4r64": ("cfg4r64", 16384, 1024, 1, 1024, 64, 65536, False, {}),
+              "n512r512": ("n512r512", 512, 256, 4, 1024, 1024, 524288, True, {}),
               "cfg2r512": ("cfg2r512", 1024, 256, 4, 1024, 1024, 524288, False, {}),
               "n512": ("n512", 512, 256, 4, 1024, 128, 65536, True, {})}
     which = sys.argv[1:] or ["cfg2"]

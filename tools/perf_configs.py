@@ -99,12 +99,12 @@ def main():
     res.append(run(torch, "cfg2 pre-overlapped", 1024, 256, 4, 1024, 512, 262144, False))
     res.append(run(torch, "cfg2 in-engine overlap", 1024, 256, 4, 1024, 512, 262144, True))
     # cfg3: N=4096, 512 bins, overlap 8, tau=0.95 -> t0d=20, B=256
-    res.append(run(torch, "cfg3 persistence stress", 4096, 512, 8, 256, 256, 32768, True, t0d=20.0))
+    res.append(run(torch, "cfg3 persistence stress", 4096, 512, 8, 256, 512, 65536, True, t0d=20.0))
     # cfg4 shape on one GPU (one channel): N=16384, 1024 bins, B=1024
     res.append(run(torch, "cfg4 one channel", 16384, 1024, 1, 1024, 32, 16384, False))
     # cfg5 sweep: K=256, overlap 4, B=1024
     for n in (512, 1024, 2048, 4096, 8192, 16384):
-        rows = {512: 524288, 1024: 262144}.get(n, 16384)   # N <= 1024: four chunks of 64 M samples (two-stream schedule)
+        rows = (1 << 28) // n                          # a 1 GiB waterfall ring at every size
         res.append(run(torch, "cfg5 sweep N=%d" % n, n, 256, 4, 1024, (rows // 1024) * 2, rows, True))
     for r in res:
         r["frac_of_hbm_peak"] = r["algorithmic_GBps"] / peak
