@@ -57,6 +57,18 @@ struct FftPlan {
 template <class P>
 __device__ __forceinline__ int pad_idx(int a) { return a + (a >> P::PADSHIFT); }
 
+/* pad_idx(base + t * STRIDE) == pad_idx(base) + pad_step<P, STRIDE>(t) for every access pattern of
+ * the kernels below: the low PADSHIFT bits of base and of t * STRIDE never carry (pass-1/2 reads:
+ * STRIDE = NB1 is a multiple of 2^PADSHIFT; pass-1 stores: base = (i-k)*R1 + k with k < R0 and
+ * STRIDE = R0 = 8 or 16; pass-0 stores: base = i*R0, STRIDE = 1, t < R0).  The compiler cannot see
+ * that, and without it every element costs a shift and an add (12 % of the instructions of the
+ * three-pass kernels, ncu); with it the element offsets are immediates. */
+template <class P, int STRIDE>
+__host__ __device__ constexpr int pad_step(int t)
+{
+	return t * STRIDE + ((t * STRIDE) >> P::PADSHIFT);
+}
+
 __device__ __forceinline__ float log_power(float2 x)
 {
 	/* display.cl:136: log10(hypot(re, im)).  re^2+im^2 cannot overflow for
@@ -135,7 +147,7 @@ fft_power_kernel(const float2 *__restrict__ in, long long hop,
 		dif<R0>(v);
 		static_for<0, R0>([&](auto tc) {
 			constexpr int t = decltype(tc)::value;
-			buf[pad_idx<P>(i * R0 + t)] = v[brev<R0>(t)];
+			buf[pad_idx<P>(i * R0) + pad_step<P, 1>(t)] = v[brev<R0>(t)];
 		});
 	}
 	sync_spectrum<P>();
@@ -150,7 +162,7 @@ fft_power_kernel(const float2 *__restrict__ in, long long hop,
 	float2 v[R1];
 #pragma unroll
 	for (int t = 0; t < R1; t++)
-		v[t] = buf[pad_idx<P>(i + t * P::NB1)];
+		v[t] = buf[pad_idx<P>(i) + pad_step<P, P::NB1>(t)];
 #pragma unroll
 	for (int t = 1; t < R1; t++)
 		v[t] = cmul(v[t], __ldg(&tw[t * PP + k]));
@@ -168,7 +180,7 @@ fft_power_kernel(const float2 *__restrict__ in, long long hop,
 		sync_spectrum<P>();                     /* all reads of pass 1 done */
 		static_for<0, R1>([&](auto tc) {
 			constexpr int t = decltype(tc)::value;
-			buf[pad_idx<P>(j + t * PP)] = v[brev<R1>(t)];
+			buf[pad_idx<P>(j) + pad_step<P, PP>(t)] = v[brev<R1>(t)];
 		});
 		sync_spectrum<P>();
 
@@ -177,7 +189,7 @@ fft_power_kernel(const float2 *__restrict__ in, long long hop,
 		const int k2 = i & (P2 - 1);
 #pragma unroll
 		for (int t = 0; t < R1; t++)
-			v[t] = buf[pad_idx<P>(i + t * P::NB1)];
+			v[t] = buf[pad_idx<P>(i) + pad_step<P, P::NB1>(t)];
 #pragma unroll
 		for (int t = 1; t < R1; t++)
 			v[t] = cmul(v[t], __ldg(&tw[P::TW1 + t * P2 + k2]));
@@ -358,7 +370,7 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 				dif<R0>(v0);
 				static_for<0, R0>([&](auto tc) {
 					constexpr int t = decltype(tc)::value;
-					bq[pad_idx<P>(lane * R0 + t)] = v0[brev<R0>(t)];
+					bq[pad_idx<P>(lane * R0) + pad_step<P, 1>(t)] = v0[brev<R0>(t)];
 				});
 			}
 		}
@@ -373,7 +385,7 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 			float2 v[R1];
 #pragma unroll
 			for (int t = 0; t < R1; t++)
-				v[t] = bq[pad_idx<P>(i1 + t * P::NB1)];
+				v[t] = bq[pad_idx<P>(i1) + pad_step<P, P::NB1>(t)];
 #pragma unroll
 			for (int t = 1; t < R1; t++)
 				v[t] = cmul(v[t], TWREG ? twreg[t] : __ldg(&tw[t * R0 + k]));
@@ -479,7 +491,7 @@ fft_power_cta_stream_kernel(const float2 *__restrict__ in, long long hop,
 			const int i = tid + q * P::T;
 			static_for<0, R0>([&](auto tc) {
 				constexpr int t = decltype(tc)::value;
-				buf[pad_idx<P>(i * R0 + t)] = v0[q][brev<R0>(t)];
+				buf[pad_idx<P>(i * R0) + pad_step<P, 1>(t)] = v0[q][brev<R0>(t)];
 			});
 		}
 		__syncthreads();
@@ -490,7 +502,7 @@ fft_power_cta_stream_kernel(const float2 *__restrict__ in, long long hop,
 		float2 v[R1];
 #pragma unroll
 		for (int t = 0; t < R1; t++)
-			v[t] = buf[pad_idx<P>(i + t * P::NB1)];
+			v[t] = buf[pad_idx<P>(i) + pad_step<P, P::NB1>(t)];
 #pragma unroll
 		for (int t = 1; t < R1; t++)
 			v[t] = cmul(v[t], __ldg(&tw[t * R0 + k]));
@@ -499,7 +511,7 @@ fft_power_cta_stream_kernel(const float2 *__restrict__ in, long long hop,
 		__syncthreads();
 		static_for<0, R1>([&](auto tc) {
 			constexpr int t = decltype(tc)::value;
-			buf[pad_idx<P>(j + t * R0)] = v[brev<R1>(t)];
+			buf[pad_idx<P>(j) + pad_step<P, R0>(t)] = v[brev<R1>(t)];
 		});
 		__syncthreads();
 
@@ -508,7 +520,7 @@ fft_power_cta_stream_kernel(const float2 *__restrict__ in, long long hop,
 		const int k2 = i & (P2 - 1);
 #pragma unroll
 		for (int t = 0; t < R1; t++)
-			v[t] = buf[pad_idx<P>(i + t * P::NB1)];
+			v[t] = buf[pad_idx<P>(i) + pad_step<P, P::NB1>(t)];
 #pragma unroll
 		for (int t = 1; t < R1; t++)
 			v[t] = cmul(v[t], __ldg(&tw[P::TW1 + t * P2 + k2]));
@@ -606,7 +618,7 @@ fft_power_half_stage_kernel(const float2 *__restrict__ in, long long hop,
 		dif<R0>(va);
 		static_for<0, R0>([&](auto tc) {
 			constexpr int t = decltype(tc)::value;
-			buf[pad_idx<P>(tid * R0 + t)] = va[brev<R0>(t)];
+			buf[pad_idx<P>(tid * R0) + pad_step<P, 1>(t)] = va[brev<R0>(t)];
 		});
 #pragma unroll
 		for (int t = 0; t < R0; t++) {
@@ -616,7 +628,7 @@ fft_power_half_stage_kernel(const float2 *__restrict__ in, long long hop,
 		dif<R0>(vb);
 		static_for<0, R0>([&](auto tc) {
 			constexpr int t = decltype(tc)::value;
-			buf[pad_idx<P>((tid + T) * R0 + t)] = vb[brev<R0>(t)];
+			buf[pad_idx<P>((tid + T) * R0) + pad_step<P, 1>(t)] = vb[brev<R0>(t)];
 		});
 		__syncthreads();
 
@@ -626,7 +638,7 @@ fft_power_half_stage_kernel(const float2 *__restrict__ in, long long hop,
 		float2 v[R1];
 #pragma unroll
 		for (int t = 0; t < R1; t++)
-			v[t] = buf[pad_idx<P>(i + t * P::NB1)];
+			v[t] = buf[pad_idx<P>(i) + pad_step<P, P::NB1>(t)];
 #pragma unroll
 		for (int t = 1; t < R1; t++)
 			v[t] = cmul(v[t], __ldg(&tw[t * R0 + k]));
@@ -635,7 +647,7 @@ fft_power_half_stage_kernel(const float2 *__restrict__ in, long long hop,
 		__syncthreads();
 		static_for<0, R1>([&](auto tc) {
 			constexpr int t = decltype(tc)::value;
-			buf[pad_idx<P>(j + t * R0)] = v[brev<R1>(t)];
+			buf[pad_idx<P>(j) + pad_step<P, R0>(t)] = v[brev<R1>(t)];
 		});
 		__syncthreads();
 
@@ -644,7 +656,7 @@ fft_power_half_stage_kernel(const float2 *__restrict__ in, long long hop,
 		const int k2 = i & (P2 - 1);
 #pragma unroll
 		for (int t = 0; t < R1; t++)
-			v[t] = buf[pad_idx<P>(i + t * P::NB1)];
+			v[t] = buf[pad_idx<P>(i) + pad_step<P, P::NB1>(t)];
 #pragma unroll
 		for (int t = 1; t < R1; t++)
 			v[t] = cmul(v[t], __ldg(&tw[P::TW1 + t * P2 + k2]));
