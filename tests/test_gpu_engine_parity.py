@@ -423,6 +423,19 @@ def test_automatic_two_stream_schedule_is_bit_identical(torch_cuda, monkeypatch)
         assert np.array_equal(outs[0][key], outs[1][key]), key
 
 
+@pytest.mark.parametrize("b", [8192, 32768])
+def test_maximum_batch_sizes(torch_cuda, b):
+    """Batches beyond the shared-memory (d, e) table (B > 4096: table read from global memory)
+    up to the largest batch the ABI accepts (32768), one call, N = 512."""
+    n, k = 512, 128
+    x = signals.noise_tones(n * b, n_fft=n, seed=500 + b, sigma=0.05)
+    eng, host, orc = _run_both(torch_cuda, dict(fft_len=n, n_bins=k, wf_rows=b, batch_max=b), [x])
+    parity.check_waterfall(host["waterfall"], orc.waterfall)
+    parity.check_histogram(host["histogram"], orc.histogram, hits_in_play=b * n)
+    parity.check_spectrum(host["spectrum"], orc.spectrum, wf_ref=orc.waterfall)
+    eng.close()
+
+
 def test_histogram_mass_property(torch_cuda):
     """From a zero histogram one call deposits, per column, exactly the mass the
     closed form predicts from hit counts summing to B: sum_bins d(hc)*(1-e(hc)).
