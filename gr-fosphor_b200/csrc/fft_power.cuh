@@ -44,9 +44,15 @@ struct FftPlan {
 	 * float2, R0*R1 apart) land in different halves of the 32 banks (ncu: 46 % of the shared
 	 * wavefronts of N = 2048 / 8192 were conflict replays with a shift of 3) */
 	static constexpr int PADSHIFT = ilog2c(R0) < 4 ? 4 : ilog2c(R0);
+	/* second level, N = 8192 only (R0 = 8, R1 = 32): the two runs of a pass-1 store are R0*R1 = 256
+	 * float2 apart, which the first level pads by 16 - the same banks again; 8 more float2 per 256
+	 * move the second run to the other half of the banks (tests/test_fft_layout.py simulates every
+	 * access of every plan) */
+	static constexpr int PADSHIFT2 = (R0_ == 8 && R1_ == 32) ? 8 : 0;
+	static constexpr int PAD2 = PADSHIFT2 ? 8 : 0;
 	/* launch bound of the plain kernel = the CTAs/SM that shared memory allows (8192: 3 CTAs at <= 80 registers) */
 	static constexpr int MIN_CTAS = R1_ == 64 ? 1 : (N_ <= 1024 ? 4 : (N_ == 2048 ? 8 : (N_ == 4096 ? 4 : (N_ == 8192 ? 3 : 1))));
-	static constexpr int SM_ELEMS = N + (N >> PADSHIFT);
+	static constexpr int SM_ELEMS = N + (N >> PADSHIFT) + (PADSHIFT2 ? PAD2 * (N >> PADSHIFT2) : 0);
 	static constexpr size_t SMEM = sizeof(float2) * (size_t)SM_ELEMS * SPB;
 	/* twiddle table: pass 1 [R1][P1] with P1 = R0, then pass 2 [R1][P2], P2 = R0*R1 */
 	static constexpr int TW1 = R1 * R0;
@@ -55,7 +61,13 @@ struct FftPlan {
 };
 
 template <class P>
-__device__ __forceinline__ int pad_idx(int a) { return a + (a >> P::PADSHIFT); }
+__device__ __forceinline__ int pad_idx(int a)
+{
+	if constexpr (P::PADSHIFT2 != 0)
+		return a + (a >> P::PADSHIFT) + P::PAD2 * (a >> P::PADSHIFT2);
+	else
+		return a + (a >> P::PADSHIFT);
+}
 
 /* pad_idx(base + t * STRIDE) == pad_idx(base) + pad_step<P, STRIDE>(t) for every access pattern of
  * the kernels below: the low PADSHIFT bits of base and of t * STRIDE never carry (pass-1/2 reads:
@@ -66,7 +78,8 @@ __device__ __forceinline__ int pad_idx(int a) { return a + (a >> P::PADSHIFT); }
 template <class P, int STRIDE>
 __host__ __device__ constexpr int pad_step(int t)
 {
-	return t * STRIDE + ((t * STRIDE) >> P::PADSHIFT);
+	return t * STRIDE + ((t * STRIDE) >> P::PADSHIFT) +
+	       (P::PADSHIFT2 ? P::PAD2 * ((t * STRIDE) >> P::PADSHIFT2) : 0);
 }
 
 __device__ __forceinline__ float log_power(float2 x)
