@@ -74,6 +74,7 @@ struct AccumArgs {
 	float mh_keep, mh_mix;    /* display.cl:303 */
 	float rho_rg;             /* fused kernel: (1-alpha)^(rows per warp step) */
 	int depth_log2;           /* fused kernel: log2 of the boxes in the stage ring */
+	int lut_staged;           /* update_kernel: the (d, e) table fits its shared memory (else read from global) */
 };
 
 /* display.cl:161-165: bin = (int)round(histo_scale * (pwr + histo_ofs)), round
@@ -416,9 +417,12 @@ __device__ __forceinline__ void update_cells(const AccumArgs &a, int block, floa
 #pragma unroll
 		for (int u = 0; u < UPD_SLICES; u++)
 			w[u] = (u < total) ? __ldcg(cnt + (size_t)u * stride) : make_uint2(0u, 0u);
-		for (int i = threadIdx.x; i <= a.batch; i += UPD_THREADS)
-			sh_lut[i] = __ldg(&a.lut[i]);
-		__syncthreads();
+		if (a.lut_staged) {
+			for (int i = threadIdx.x; i <= a.batch; i += UPD_THREADS)
+				sh_lut[i] = __ldg(&a.lut[i]);
+			__syncthreads();
+		}
+		const float2 *lut = a.lut_staged ? sh_lut : a.lut;   /* batches beyond ~8 K rows: table too big to stage */
 		if (!live_thread)
 			return;
 		float4 hv = hv0;
@@ -446,10 +450,10 @@ __device__ __forceinline__ void update_cells(const AccumArgs &a, int block, floa
 						const bool idle = (hc0 | hc1 | hc2 | hc3) == 0 &&
 						                  fmaxf(fmaxf(hv.x, hv.y), fmaxf(hv.z, hv.w)) <= 0.01f;
 						if (!__all_sync(0xffffffffu, idle)) {
-							hv.x = rise_decay(hv.x, hc0, sh_lut);
-							hv.y = rise_decay(hv.y, hc1, sh_lut);
-							hv.z = rise_decay(hv.z, hc2, sh_lut);
-							hv.w = rise_decay(hv.w, hc3, sh_lut);
+							hv.x = rise_decay(hv.x, hc0, lut);
+							hv.y = rise_decay(hv.y, hc1, lut);
+							hv.z = rise_decay(hv.z, hc2, lut);
+							hv.w = rise_decay(hv.w, hc3, lut);
 						}
 						hc0 = hc1 = hc2 = hc3 = 0;
 						in_call = 0;

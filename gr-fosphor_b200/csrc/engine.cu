@@ -35,6 +35,7 @@ constexpr int MAX_SLICES = 128;  /* (call, row-split) slices folded by one count
 constexpr size_t CNT_BUDGET = (size_t)1 << 30;   /* bytes of u16 hit-count slices kept on the device (split kernels) */
 constexpr int N_CHUNK_EV = 64;   /* chunks in flight tracked by the two-stream schedule */
 constexpr size_t UPD_SMEM_MAX = 96 * 1024;   /* dynamic shared memory of update_kernel */
+constexpr size_t UPD_LUT_SMEM_MAX = 64 * 1024;   /* ... of which the (d, e) table: batches up to 8191 rows */
 
 struct BatchTables {
 	int batch = -1;
@@ -653,7 +654,8 @@ int launch_accumulate(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cuda
 	const size_t per_block = (size_t)UPD_THREADS * UPD_CELLS;   /* N is a multiple of 512: no straddling */
 	const int cell_blocks = (int)((cells + per_block - 1) / per_block);
 	const int col_blocks = (e->p.fft_len + UPD_COLS - 1) / UPD_COLS;
-	const size_t lut_smem = sizeof(float2) * (size_t)(batch + 1);
+	a.lut_staged = sizeof(float2) * (size_t)(batch + 1) <= UPD_LUT_SMEM_MAX;
+	const size_t lut_smem = a.lut_staged ? sizeof(float2) * (size_t)(batch + 1) : 0;
 	/* partials staged per pass by the column blocks */
 	const int blocks_per_call = (batch + ROWBLOCK - 1) / ROWBLOCK;
 	const int cap = blocks_per_call > UPD_PARTS ? blocks_per_call : UPD_PARTS / blocks_per_call * blocks_per_call;
@@ -1049,6 +1051,8 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 	}
 	{
 		size_t upd = sizeof(float2) * (size_t)(p.batch_max + 1);
+		if (upd > UPD_LUT_SMEM_MAX)
+			upd = UPD_LUT_SMEM_MAX;       /* larger tables are read from global memory */
 		const size_t parts = sizeof(float) * 2 * UPD_COLS * (size_t)((p.batch_max + ROWBLOCK - 1) / ROWBLOCK);
 		if (upd < parts) upd = parts;
 		if (upd < UPD_SMEM_MAX) upd = UPD_SMEM_MAX;
