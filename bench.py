@@ -477,6 +477,10 @@ def run_reference(args):
                                   "step = 8 calls + finish; reference fixed at 128 bins"},
            "cpu_baseline": {"value": value, "unit": "Mcomplex-samples/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "Mcomplex-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if kind == "reference" and not args.no_cpu:
+        # the box has no CPU OpenCL platform, so the reference's own kernels ran on the GPU; for a
+        # host-cores figure next to it: the oracle port (same arithmetic, OpenMP), bounded sample
+        out["cpu_port"] = cpu_baseline_port(seconds_budget=8.0)
     print(json.dumps(out))
 
 
