@@ -617,6 +617,23 @@ __host__ __device__ inline unsigned acc_tile_bytes(int K, int cols)
 	return a;
 }
 
+/* Stage-ring safety.  A warp waits for box n on full[n % depth] by PARITY, which only tells the
+ * current phase of that barrier from the previous one: the wait is correct only if box n - depth
+ * has already landed when the warp starts waiting - otherwise it passes on the older box (wrong
+ * data, a spurious arrival on empty[], and in the end a producer that waits forever).  That is
+ * guaranteed when
+ *   - the launch has no more boxes than the ring, or
+ *   - depth is a multiple of the boxes of one synchronisation group: box n and box n - depth then sit
+ *     at the same position of their groups, are consumed by the same warps, in program order, or
+ *   - the ring spans two groups: box n - depth belongs to group g-2 or older, which every counter
+ *     warp has finished before any warp may start group g (hits_free barrier).
+ * Batches with more boxes per call than the ring holds (B = 32768: 128 boxes, ring of 32) violate all
+ * three - warps 4..15 start out waiting two and three phases ahead - and take the plain-load path. */
+__host__ __device__ inline bool acc_ring_safe(long long depth, long long boxes_per_group, long long boxes_total)
+{
+	return boxes_total <= depth || depth % boxes_per_group == 0 || depth >= 2 * boxes_per_group;
+}
+
 template <int COLS, int FW, int UW, int BOXR, int GC = 1>
 struct FusedCfg {
 	static_assert(GC == 1 || GC == 2 || GC == 4, "calls per synchronisation group");

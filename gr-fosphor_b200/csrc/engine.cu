@@ -482,6 +482,11 @@ cudaError_t fused_launch(fosphor_cu *e, AccumArgs a, cudaStream_t st)
 	while (dlog > 0 && (1ll << (dlog - 1)) >= boxes)
 		dlog--;
 	a.depth_log2 = dlog;
+	if constexpr (LOAD != 0) {
+		/* parity waits on the stage ring are only sound for these shapes (accumulate.cuh: acc_ring_safe) */
+		if (!acc_ring_safe(1ll << dlog, (long long)GC * (a.batch / BOXR), boxes))
+			return fused_launch<COLS, FW, UW, 16, 16, 0, GC>(e, a, st);
+	}
 	const size_t smem = C::smem(a.n_bins, a.batch, LOAD != 0, dlog);
 	static size_t configured = 0;          /* per kernel instantiation */
 	if (smem > configured) {

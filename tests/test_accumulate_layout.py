@@ -77,3 +77,70 @@ def test_boxes_and_sharers():
             assert len(users) == 3 * batch // boxr
             for box, us in users.items():
                 assert len(us) == sharers, (batch, boxr, box)
+
+
+def ring_safe(depth, boxes_per_group, boxes_total):
+    """accumulate.cuh: acc_ring_safe"""
+    return boxes_total <= depth or depth % boxes_per_group == 0 or depth >= 2 * boxes_per_group
+
+
+def _waits(batch, boxr, fw, gc, n_calls):
+    """program of every counter warp: [(group, box index)] in order"""
+    rv = rows_per_vwarp(batch)
+    nv = (batch + rv - 1) // rv
+    ch = min(rv, boxr)
+    progs = {w: [] for w in range(fw)}
+    n_groups = (n_calls + gc - 1) // gc
+    for grp in range(n_groups):
+        ncg = min(gc, n_calls - grp * gc)
+        for warp in range(fw):
+            p = warp
+            while p < ncg * nv:
+                ci, v = divmod(p, nv)
+                call = grp * gc + ci
+                lo = v * rv
+                rows = min(batch - lo, rv)
+                for c0 in range(0, rows, ch):
+                    progs[warp].append((grp, (call * batch + lo + c0) // boxr))
+                p += fw
+    return progs
+
+
+def test_stage_ring_parity_waits_are_sound():
+    """A parity wait for box n is sound only if box n - depth has landed before the wait starts in
+    EVERY schedule: the same warp consumed it earlier, or it belongs to group g-2 or older (all
+    counters finished that group before any warp may enter group g).  Whenever the host rule says
+    "safe", that must hold for every wait of every warp; the shapes that hung (B = 32768 on a ring of
+    32 boxes, B = 8192 on a ring of 16) must be rejected."""
+    checked = rejected = 0
+    for fw in (8, 16):
+        for gc in (1, 2, 4):
+            for batch in [16, 64, 256, 528, 1024, 1040, 2048, 2112, 4096, 8192, 32768]:
+                boxr = box_rows(batch, 0, 1 << 20)
+                if boxr == 0:
+                    continue
+                bpc = batch // boxr
+                for n_calls in (1, 3, 9):
+                    total = n_calls * bpc
+                    progs = _waits(batch, boxr, fw, gc, n_calls)
+                    for dlog in range(0, 10):
+                        depth = 1 << dlog
+                        if depth > 8192 // boxr:
+                            break
+                        if not ring_safe(depth, gc * bpc, total):
+                            rejected += 1
+                            continue
+                        checked += 1
+                        for warp, prog in progs.items():
+                            mine = set()
+                            for grp, n in prog:
+                                old = n - depth
+                                if old >= 0:
+                                    old_grp = (old // bpc) // gc
+                                    assert old in mine or old_grp <= grp - 2, (batch, boxr, fw, gc, n_calls, depth, warp, n)
+                                mine.add(n)
+    assert checked > 100 and rejected > 10
+    assert not ring_safe(32, 128, 128)      # B = 32768, 256-row boxes, ring of 32
+    assert not ring_safe(16, 32, 32)        # B = 8192, ring of 16
+    assert ring_safe(16, 4, 256)            # bench: B = 1024
+    assert ring_safe(4, 4, 128)             # cfg3: four calls of one box per group
