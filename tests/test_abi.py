@@ -90,6 +90,30 @@ def test_no_gpu_fails_loudly():
         FosphorCL(build.LIB)
 
 
+def test_c99_caller_builds_against_the_headers_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/dropin_min.c: a plain C99 translation unit (-pedantic) that includes the two public
+    headers, links libfosphor_b200.so and drives the seven fosphor_cl_* entry points the way
+    lib/fosphor/fosphor.c does.  Without a CUDA device init must report -EIO (exit code 2); with one
+    the burst is processed (exit code 0)."""
+    import shutil
+    import subprocess
+    import torch
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from gr_fosphor_b200 import build
+    lib = build.build()
+    exe = str(tmp_path / "dropin_min")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "dropin_min.c"), "-o", exe,
+                           "-L", os.path.dirname(lib), "-lfosphor_b200", "-Wl,-rpath," + os.path.dirname(lib), "-lm"])
+    rc = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert rc.returncode == 0, rc.stderr
+    else:
+        assert rc.returncode == 2, (rc.returncode, rc.stderr)
+        assert "-EIO" in rc.stderr
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "gr-fosphor_b200")
     for dirpath, _, files in os.walk(pkg):
