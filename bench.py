@@ -4,27 +4,31 @@
   python bench.py --gpus N --steps K --warmup W            (this repo's CUDA engine)
   python bench.py --impl reference --gpus N --steps K ...  (the reference's own path)
 
-Workload = BASELINE.json configs[1]: N=1024 FFT, 256 power bins, overlap 4,
-continuous 100 Msps synthetic IQ, calls of B=1024 spectra.  One STEP is one
-second of that signal: 1e8 raw samples -> 4e8 samples entering
-the FFT = 384 calls of 1024 spectra (393,216 spectra, 402.7 Msamples), so
-1000 / ms_per_step is the real-time headroom.  The stream is the
-pre-overlapped one the reference's fosphor_cl_process() receives (overlap_cc
-upstream, lib/overlap_cc_impl.cc:64-79); the in-engine-overlap variant (raw
-stream, hop = N/4) is reported next to it under "overlap_in_engine".
+Workload = BASELINE.json configs[1]: N=1024 FFT, overlap 4, continuous 100 Msps synthetic IQ
+in calls of B=1024 spectra (the pre-overlapped stream fosphor_cl_process() receives; overlap_cc
+upstream, lib/overlap_cc_impl.cc:64-79).
 
-Metric: Mcomplex-samples/s into the FFT (whole job, all GPUs).  `value` is
-device-resident (inputs already in HBM, rotating over a pool larger than L2),
-`e2e` goes through the C ABI with HOST buffers: H2D of every sample and the
-D2H read-back of waterfall + histogram + spectrum each step inside the timed
-region.  Multi-GPU: one engine (one channel) per GPU, weak scaling, one NCCL
-max all-reduce of the max-hold trace per step (BASELINE.json configs[3]).
+`value` (device-resident, 256 power bins as BASELINE names): one PASS is one second of that
+signal - 1e8 raw samples -> 4e8 samples into the FFT = 384 calls of 1024 spectra - and one STEP
+is `--passes` (default 50) passes over two alternating 3.2 GB input buffers, so that the K timed
+steps cover about a second of GPU time.  The waterfall has the reference's 1024 rows
+(cl.c:430-432); how many calls one launch pair folds is the engine's business (its log-power
+scratch ring), not the display's.  The timed region closes after fosphor_cu_flush() has joined
+the engine's accumulate stream.
+
+`e2e` (the headline against the reference arm) mirrors `--impl reference` exactly: the seven
+fosphor_cl_* symbols of the drop-in library, PAGEABLE host input as the unmodified sink hands
+it (lib/fifo.cc:17-21), the reference's fixed geometry (128 bins, 1024 rows), one sink frame =
+8 process calls of 1024 spectra + fosphor_cl_finish (lib/base_sink_c_impl.cc:133-175) with the
+4.5 MiB result read-back, H2D of every sample inside the timed region.
+
+Multi-GPU: one engine (one channel) per GPU, weak scaling, one NCCL max all-reduce of the
+max-hold trace per pass (BASELINE.json configs[3]) on a side stream.
 """
 import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -36,9 +40,19 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-N_FFT, N_BINS, OVERLAP, BATCH, CALLS_PER_STEP = 1024, 256, 4, 1024, 384
-WF_ROWS = 262144  # device waterfall ring (1 GiB): 256 calls; the engine's two-stream schedule then works in chunks of 64 calls
-REF_CALLS_PER_STEP = 8   # reference arm: one sink frame (base_sink_c_impl.cc:133-146) per step
+N_FFT, N_BINS, OVERLAP, BATCH, CALLS_PER_PASS = 1024, 256, 4, 1024, 384
+WF_ROWS = 1024            # reference geometry (cl.c:430-432)
+FRAME_CALLS = 8           # one sink frame (base_sink_c_impl.cc:133-146)
+REF_BINS = 128            # display.cl:96: the fosphor_cl_* boundary is fixed at 128 bins
+
+# identical in both arms (the driver compares them)
+CONFIG = {
+    "workload": "cfg2: N=1024 FFT, overlap=4 (pre-overlapped stream, r=1), continuous synthetic IQ in calls of "
+                "B=1024 spectra",
+    "fft_len": N_FFT, "overlap": OVERLAP, "batch": BATCH, "wf_rows": WF_ROWS,
+    "e2e_frame": "8 fosphor_cl_process calls of 1024 spectra + fosphor_cl_finish, pageable host input, "
+                 "128 bins / 1024 waterfall rows (the boundary's fixed geometry)",
+}
 
 
 def algorithmic_bytes_per_call(n, k, b, r):
@@ -60,10 +74,10 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled through NVML every ~5 ms during the timed region."""
+    """SM clock, power and throttle reasons sampled through NVML every ~5 ms during the timed region."""
 
     def __init__(self, index):
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.index, self.samples, self.power, self.reasons, self.max_mhz = index, [], [], set(), None
         self._stop = threading.Event()
         self.thr = None
 
@@ -89,6 +103,7 @@ class ClockSampler:
                 while not self._stop.is_set():
                     try:
                         self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
                         r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
                         for k, bit in names.items():
                             if r & bit:
@@ -106,7 +121,9 @@ class ClockSampler:
         if self.thr:
             self.thr.join(timeout=2)
         sm = self.samples
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_mhz_min": min(sm) if sm else None,
+                "sm_max_mhz": self.max_mhz, "power_w_max": max(self.power) if self.power else None,
+                "power_w_median": statistics.median(self.power) if self.power else None,
                 "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
@@ -127,12 +144,12 @@ def synth_stream_torch(torch, n_samples, seed, device):
     return x
 
 
-def cpu_baseline_port(seconds_budget=12.0):
+def cpu_baseline_port(seconds_budget=12.0, n_bins=N_BINS):
     """CPU oracle (f32 FFT variant, OpenMP over all host threads) on a bounded
-    sample of the same workload: whole steps of 8 calls x 1024 spectra."""
+    sample of the same workload: calls of 1024 spectra."""
     import oracle_lib
     import signals
-    orc = oracle_lib.Oracle(fft_len=N_FFT, n_bins=N_BINS, wf_rows=1024, fft_f32=True)
+    orc = oracle_lib.Oracle(fft_len=N_FFT, n_bins=n_bins, wf_rows=1024, fft_f32=True)
     x = signals.noise_tones(N_FFT * BATCH, seed=2).astype(np.complex64)
     orc.process(x)                       # warm-up call
     t0, calls = time.perf_counter(), 0
@@ -146,10 +163,43 @@ def cpu_baseline_port(seconds_budget=12.0):
     msps = calls * BATCH * N_FFT / el / 1e6
     threads = oracle_lib.lib().fosphor_oracle_threads()
     return {"value": msps, "unit": "Mcomplex-samples/s", "cores": int(threads), "kind": "port",
-            "sample": "%d calls of %d spectra (N=%d, K=%d), f32 FFT oracle, %.1f s" % (calls, BATCH, N_FFT, N_BINS, el)}
+            "sample": "%d calls of %d spectra (N=%d, K=%d), f32 FFT oracle, %.1f s" % (calls, BATCH, N_FFT, n_bins, el)}
 
 
-def dist_setup(args):
+def bind_cpus(local, local_world):
+    """Best effort: keep this rank's threads (and the first touch of its page-locked buffers) on the
+    cores next to its GPU - or, when the platform reports no locality, on its own share of the
+    cores - so that 8 ranks do not fight over the same ones."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        import torch
+        prop = torch.cuda.get_device_properties(local)
+        near, node = None, -1
+        try:
+            bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+            base = "/sys/bus/pci/devices/" + bdf
+            node = int(open(base + "/numa_node").read())
+            if node >= 0:
+                cl = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+                near = set()
+                for part in cl.split(","):
+                    lo, _, hi = part.partition("-")
+                    near.update(range(int(lo), int(hi or lo) + 1))
+        except Exception:
+            near = None
+        pool = [c for c in allowed if near is None or c in near] or allowed
+        # ranks that share a pool split it
+        per = max(1, len(pool) // max(1, local_world))
+        mine = pool[(local * per) % len(pool):(local * per) % len(pool) + per] or pool
+        if local_world > 1:
+            os.sched_setaffinity(0, mine)
+        return {"numa_node": node, "cpus": "%d-%d (%d)" % (mine[0], mine[-1], len(mine)) if local_world > 1
+                else "all %d" % len(allowed)}
+    except Exception as exc:
+        return {"error": str(exc)}
+
+
+def dist_setup():
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -165,75 +215,92 @@ def dist_setup(args):
 
 def run_b200(args):
     import torch
+    from gr_fosphor_b200 import build
+    from gr_fosphor_b200.dropin import FosphorCL
     from gr_fosphor_b200.engine import Fosphor
 
-    world, rank, local, dist = dist_setup(args)
+    world, rank, local, dist = dist_setup()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    cpu_bind = bind_cpus(local, local_world)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # a real (non-default) stream: the engine enqueues on it and torch.cuda.Event times it
     stream = torch.cuda.Stream(device=dev)
+    comm = torch.cuda.Stream(device=dev) if dist is not None else None
     torch.cuda.set_stream(stream)
     peak, peak_src = measured_peaks()
 
-    n, k, b, calls = N_FFT, N_BINS, BATCH, CALLS_PER_STEP
-    spectra_per_step = calls * b
-    samples_per_step = spectra_per_step * n
+    n, k, b, calls = N_FFT, N_BINS, BATCH, CALLS_PER_PASS
+    passes = args.passes
+    spectra_per_pass = calls * b
+    samples_per_pass = spectra_per_pass * n
+    samples_per_step = samples_per_pass * passes
     hop = n // OVERLAP
 
-    wf_rows = args.wf_rows
-
-    def make_engine(rows, mode):
-        """mode None: the engine's default schedule (automatic: two streams when the ring holds four
-        chunks of >= 32 M samples); "0": every kernel on one stream (kernels timed
-        alone, clean per-kernel event timing)."""
+    def make_engine(mode=None, **kw):
+        """mode None: the engine's default schedule (automatic: two streams when its log-power ring
+        holds four chunks of >= 32 M samples); "0": every kernel on one stream (kernels
+        timed alone, clean per-kernel event timing)."""
         old = os.environ.get("FOSPHOR_B200_OVERLAP")
         if mode is None:
             os.environ.pop("FOSPHOR_B200_OVERLAP", None)
         else:
             os.environ["FOSPHOR_B200_OVERLAP"] = mode
         try:
-            return Fosphor(fft_len=n, n_bins=k, wf_rows=rows, device=local, stream=stream.cuda_stream)
+            cfg = dict(fft_len=n, n_bins=k, wf_rows=args.wf_rows, device=local, stream=stream.cuda_stream)
+            cfg.update(kw)
+            return Fosphor(**cfg)
         finally:
             if old is None:
                 os.environ.pop("FOSPHOR_B200_OVERLAP", None)
             else:
                 os.environ["FOSPHOR_B200_OVERLAP"] = old
 
-    eng = make_engine(wf_rows, None)
+    eng = make_engine()
 
     # ---- inputs: two distinct seconds of signal, raw and pre-overlapped (3.2 GB each >> L2) ----
-    pool_n = raw_pool_n = 2
-    raw_len = (spectra_per_step - 1) * hop + n
-    raws = [synth_stream_torch(torch, raw_len, 1000 * rank + 2 + i, dev) for i in range(raw_pool_n)]
+    raw_len = (spectra_per_pass - 1) * hop + n
+    raws = [synth_stream_torch(torch, raw_len, 1000 * rank + 2 + i, dev) for i in range(2)]
     # what overlap_cc would emit: [spectra][N] windows hopping N/4
     pool = [r.unfold(0, n, hop).permute(0, 2, 1).contiguous().view(-1, 2) for r in raws]
     maxhold = torch.empty(n, dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
 
-    def step_device(i, pre_overlapped=True):
-        if pre_overlapped:
-            eng.process_device_multi(pool[i % pool_n].data_ptr(), calls, b, n)
-        else:
-            eng.process_device_multi(raws[i % raw_pool_n].data_ptr(), calls, b, hop)
-        if dist is not None:                          # BASELINE configs[3]: reduced max-hold
-            eng.export_maxhold(maxhold.data_ptr())
+    def reduce_maxhold(e):
+        """BASELINE configs[3]: reduced max-hold, on a side stream - the engine's FFT / accumulate
+        pipeline is not drained for it (fosphor_cu_export_maxhold_on)"""
+        e.export_maxhold_on(maxhold.data_ptr(), comm.cuda_stream)
+        with torch.cuda.stream(comm):
             dist.all_reduce(maxhold, op=dist.ReduceOp.MAX)
 
-    def timed(fn, steps, warmup):
+    def timed(e, one_pass, steps, warmup, n_passes):
+        """K steps of n_passes passes; CUDA events on the engine's stream, after the accumulate
+        stream (and the comm stream) have been joined into it; max over ranks."""
+        def step(i):
+            for q in range(n_passes):
+                one_pass(e, i * n_passes + q)
+                if dist is not None:
+                    reduce_maxhold(e)
         for i in range(warmup):
-            fn(i)
+            step(i)
+        e.flush()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
             torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = e.launch_count
         e0.record(stream)
         for i in range(steps):
-            fn(warmup + i)
+            step(warmup + i)
+        e.flush()                                   # order `stream` after the accumulate stream
+        if comm is not None:
+            stream.wait_stream(comm)
         e1.record(stream)
         torch.cuda.synchronize()
+        launches = e.launch_count - l0
         if dist is not None:
             dist.barrier()
             torch.cuda.synchronize()
@@ -242,44 +309,58 @@ def run_b200(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms
+        return ms, launches
 
-    # ---- device-resident headline (clock sampling + per-kernel profiling) ----
+    def pass_pre(e, i):
+        e.process_device_multi(pool[i % 2].data_ptr(), calls, b, n)
+
+    def pass_raw(e, i):
+        e.process_device_multi(raws[i % 2].data_ptr(), calls, b, hop)
+
+    # ---- device-resident headline ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = eng.launch_count
-    ms = timed(lambda i: step_device(i, True), args.steps, args.warmup)
-    launches = eng.launch_count - launches0
+    ms, launches = timed(eng, pass_pre, args.steps, args.warmup, passes)
     clocks = sampler.stop() if rank == 0 else None
-    launches_timed = launches * args.steps // (args.steps + args.warmup)
     value = world * args.steps * samples_per_step / (ms * 1e-3) / 1e6
+    ring_rows = eng.host_feed_stats()["ring_rows"]
 
     # per-kernel durations while co-running (default schedule): event pairs around each launch
+    prof_steps, prof_passes = 2, min(passes, 5)
     eng.profile(True)
-    prof_steps = min(args.steps, 5)
-    timed(lambda i: step_device(i, True), prof_steps, 0)
+    timed(eng, pass_pre, prof_steps, 0, prof_passes)
     prof_co = eng.profile_read()
     eng.profile(False)
-    step_bytes = calls * algorithmic_bytes_per_call(n, k, b, 1.0)
+    step_bytes = passes * calls * algorithmic_bytes_per_call(n, k, b, 1.0)
+
+    # ---- in-engine overlap variant (raw stream, hop = N/4), same engine ----
+    side_steps, side_passes = max(2, args.steps // 4), min(passes, 10)
+    ms_hop, _ = timed(eng, pass_raw, side_steps, 1, side_passes)
+    value_hop = world * side_steps * side_passes * samples_per_pass / (ms_hop * 1e-3) / 1e6
 
     # ---- the same workload with every kernel on one stream: kernels timed ALONE ----
-    eng_default = eng
-    eng = make_engine(wf_rows, "0")
-    ms_one = timed(lambda i: step_device(i, True), args.steps, args.warmup)
-    eng.profile(True)
-    timed(lambda i: step_device(i, True), prof_steps, 0)
-    prof = eng.profile_read()
-    eng.profile(False)
-    eng.close()
-    eng = eng_default
+    eng1 = make_engine("0")
+    ms_one, _ = timed(eng1, pass_pre, side_steps, 1, side_passes)
+    eng1.profile(True)
+    timed(eng1, pass_pre, prof_steps, 0, prof_passes)
+    prof = eng1.profile_read()
+    eng1.profile(False)
+    eng1.close()
+    # ---- no folding at all: one launch pair per call of 1024 spectra (what a caller that hands the
+    #      engine one call at a time gets from device-resident input) ----
+    engu = make_engine(scratch_rows=-1)
+    ms_unf, _ = timed(engu, pass_pre, side_steps, 1, side_passes)
+    engu.close()
+    per_pass = lambda t_ms: t_ms / (side_steps * side_passes)      # noqa: E731
     fft_ms = prof["fft_ms"] / max(1, prof["fft_launches"])
     count_ms = prof["count_ms"] / max(1, prof["count_launches"])
     update_ms = prof["update_ms"] / max(1, prof["update_launches"])
-    spectra_per_fft_launch = spectra_per_step * prof_steps // max(1, prof["fft_launches"])
+    prof_spectra = spectra_per_pass * prof_steps * prof_passes
+    spectra_per_fft_launch = prof_spectra // max(1, prof["fft_launches"])
     fft_bytes = fft_kernel_bytes(n, spectra_per_fft_launch, 1.0)
     achieved = fft_bytes / (fft_ms * 1e-3) / 1e9
-    spectra_per_fft_launch_co = spectra_per_step * prof_steps // max(1, prof_co["fft_launches"])
+    spectra_per_fft_launch_co = prof_spectra // max(1, prof_co["fft_launches"])
     fft_ms_co = prof_co["fft_ms"] / max(1, prof_co["fft_launches"])
     acc_ms_co = (prof_co["count_ms"] / max(1, prof_co["count_launches"]) +
                  prof_co["update_ms"] / max(1, prof_co["update_launches"]))
@@ -293,78 +374,32 @@ def run_b200(args):
         # ncu capture was taken at 65536 spectra per launch: scale to this run's launch size
         traffic = tj.get("dram_bytes_per_launch") * spectra_per_fft_launch / tj.get("spectra_per_launch", 65536)
         acc_traffic_per_call = tj.get("accumulate_dram_bytes_per_call")
-    one = {"value": world * args.steps * samples_per_step / (ms_one * 1e-3) / 1e6,
-           "unit": "Mcomplex-samples/s", "ms_per_step": ms_one / args.steps,
-           "step_frac": step_bytes / (ms_one / args.steps * 1e-3) / 1e9 / peak,
+    pass_bytes = calls * algorithmic_bytes_per_call(n, k, b, 1.0)
+    one = {"value": world * samples_per_pass / (per_pass(ms_one) * 1e-3) / 1e6,
+           "unit": "Mcomplex-samples/s", "ms_per_pass": per_pass(ms_one),
+           "step_frac": pass_bytes / (per_pass(ms_one) * 1e-3) / 1e9 / peak,
            "fft_share_of_kernel_time": fft_ms * prof["fft_launches"] /
            max(1e-9, prof["fft_ms"] + prof["count_ms"] + prof["update_ms"]),
            "note": "FOSPHOR_B200_OVERLAP=0: FFT and accumulate launches back to back on one stream; the per-kernel "
                    "numbers of `roofline` come from this pass (kernels timed alone)"}
+    unfolded = {"value": world * samples_per_pass / (per_pass(ms_unf) * 1e-3) / 1e6, "unit": "Mcomplex-samples/s",
+                "ms_per_pass": per_pass(ms_unf),
+                "step_frac": pass_bytes / (per_pass(ms_unf) * 1e-3) / 1e9 / peak,
+                "note": "scratch_rows=-1: the 1024-row waterfall is the ring, one FFT + one accumulate launch per "
+                        "call of 1024 spectra (round-1 behaviour at the reference geometry)"}
 
-    # ---- in-engine overlap variant (raw stream, hop = N/4) ----
-    ms_hop = timed(lambda i: step_device(i, False), args.steps, args.warmup)
-    value_hop = world * args.steps * samples_per_step / (ms_hop * 1e-3) / 1e6
-
-    # ---- e2e through the C ABI with host buffers ----
-    h_pool = [torch.empty((samples_per_step, 2), dtype=torch.float32).pin_memory()]
-    h_pool[0].copy_(pool[0])
-    h_raw = [torch.empty((raw_len, 2), dtype=torch.float32).pin_memory()]
-    h_raw[0].copy_(raws[0])
-    torch.cuda.synchronize()
-    call_len = b * n
-    r_wf = torch.empty((1024, n), dtype=torch.float32).pin_memory()
-    r_hist = torch.empty((k, n), dtype=torch.float32).pin_memory()
-    r_spec = torch.empty((2, n, 2), dtype=torch.float32).pin_memory()
-
-    def finish_e2e():
-        rc = eng.finish_into(r_wf.data_ptr(), r_hist.data_ptr(), r_spec.data_ptr())
-        assert rc == 1
-
-    def step_e2e(i):
-        base = h_pool[0].data_ptr()
-        for c in range(calls):
-            eng.process_host_ptr(base + 8 * c * call_len, call_len)
-        if dist is not None:
-            eng.export_maxhold(maxhold.data_ptr())
-            dist.all_reduce(maxhold, op=dist.ReduceOp.MAX)
-        finish_e2e()
-
-    def step_e2e_raw(i):
-        eng.process_host_raw_ptr(h_raw[0].data_ptr(), calls, b, hop)
-        if dist is not None:
-            eng.export_maxhold(maxhold.data_ptr())
-            dist.all_reduce(maxhold, op=dist.ReduceOp.MAX)
-        finish_e2e()
-
-    def timed_host(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for i in range(steps):
-            fn(warmup + i)
-        torch.cuda.synchronize()
-        el = (time.perf_counter() - t0) * 1e3
-        if dist is not None:
-            t = torch.tensor([el], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            el = float(t.item())
-        return el
-
-    e2e_steps = max(2, min(args.steps, 4))
-    del pool, raws
+    # ---- other BASELINE configs, device-resident, one GPU ----
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del pool
+        torch.cuda.empty_cache()
+        extras = run_extras(torch, dev, stream, local, peak, raws)
+    del raws
+    pool = None
     torch.cuda.empty_cache()
-    eng_dev = eng
-    eng = make_engine(1024, None)    # reference-sized ring
-    ms_e2e = timed_host(step_e2e, e2e_steps, 1)
-    e2e = world * e2e_steps * samples_per_step / (ms_e2e * 1e-3) / 1e6
-    ms_e2e_raw = timed_host(step_e2e_raw, e2e_steps, 1)
-    e2e_raw = world * e2e_steps * samples_per_step / (ms_e2e_raw * 1e-3) / 1e6
-    d2h = 4 * (1024 * n + k * n + 4 * n)
-    eng.close()
-    eng = eng_dev
+
+    # ---- e2e through the reference's own boundary, host buffers ----
+    e2e = run_e2e(torch, dist, dev, local, world, args, build.LIB, FosphorCL, Fosphor, stream)
 
     cpu = cpu_baseline_port() if (rank == 0 and world == 1 and not args.no_cpu) else None
 
@@ -376,15 +411,20 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "realtime_factor_100Msps": 1000.0 / (ms / args.steps),
-            "config": {"workload": "cfg2: N=1024, 256 bins, overlap=4 (pre-overlapped stream, r=1), B=1024 "
-                                   "spectra/call, step = 1 s of 100 Msps IQ = 384 calls = 393216 spectra",
-                       "fft_len": n, "n_bins": k, "overlap": OVERLAP, "batch": b, "calls_per_step": calls,
-                       "wf_rows": wf_rows,
-                       "schedule": "engine default (automatic): two streams, chunks of wf_rows/4 rows",
-                       "l2": "each step streams a %d MiB input (two alternating buffers), far larger than the 126 MB L2" % (samples_per_step * 8 // 2**20),
-                       "multi_gpu": "one channel per GPU, NCCL max all-reduce of max-hold per step" if world > 1 else "single"},
-            "gpu_launches": int(launches_timed),
+            "realtime_factor_100Msps": 1000.0 * passes / (ms / args.steps),
+            "config": CONFIG,
+            "details": {"value": "device-resident, %d power bins, step = %d passes of 1 s of 100 Msps IQ "
+                                 "(384 calls = 393216 spectra each)" % (k, passes),
+                        "n_bins": k, "calls_per_pass": calls, "passes_per_step": passes,
+                        "timed_region_s": ms * 1e-3, "wf_rows": args.wf_rows, "log_power_ring_rows": ring_rows,
+                        "schedule": "engine default (automatic): two streams, chunks of ring/4 rows; "
+                                    "timed region closed after fosphor_cu_flush()",
+                        "l2": "each pass streams a %d MiB input (two alternating buffers), far larger than the "
+                              "126 MB L2" % (samples_per_pass * 8 // 2**20),
+                        "multi_gpu": ("one channel per GPU, NCCL max all-reduce of max-hold per pass on a side "
+                                      "stream") if world > 1 else "single",
+                        "cpu_binding": cpu_bind},
+            "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "fft_power_stream_kernel<Plan1024, TWREG>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -394,31 +434,207 @@ def run_b200(args):
                                   "accumulate kernel of the previous chunk, see `concurrent`",
                          "bytes_per_launch": fft_bytes, "ms_per_launch": fft_ms,
                          "spectra_per_launch": spectra_per_fft_launch,
-                         "accumulate_kernel": "accumulate_fused_kernel<COLS=8, 16 counter + 8 updater warps, 256-row TMA boxes> (count + rise/decay + live + max-hold, one launch)",
+                         "accumulate_kernel": "accumulate_fused_kernel<COLS=8, 16 counter + 8 updater warps, 256-row "
+                                              "TMA boxes> (count + rise/decay + live + max-hold, one launch)",
                          "accumulate_ms_per_launch": count_ms + update_ms,
+                         "accumulate_achieved_GBps": 4.0 * n * spectra_per_fft_launch / ((count_ms + update_ms) * 1e-3) / 1e9,
                          "concurrent": {"schedule": "FFT of chunk c+1 beside the accumulate kernel of chunk c (two streams)",
                                         "spectra_per_launch": spectra_per_fft_launch_co,
                                         "fft_ms_per_launch": fft_ms_co, "accumulate_ms_per_launch": acc_ms_co,
                                         "fft_achieved_GBps": fft_kernel_bytes(n, spectra_per_fft_launch_co, 1.0) / (fft_ms_co * 1e-3) / 1e9,
                                         "step_dram_GBps": None if traffic is None or acc_traffic_per_call is None else
-                                        (traffic / spectra_per_fft_launch * spectra_per_step + acc_traffic_per_call * calls) /
-                                        (ms / args.steps * 1e-3) / 1e9},
+                                        (traffic / spectra_per_fft_launch * spectra_per_pass + acc_traffic_per_call * calls) /
+                                        (ms / args.steps / passes * 1e-3) / 1e9},
                          "step_algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                          "step_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
-            "e2e": {"value": e2e, "unit": "Mcomplex-samples/s",
-                    "h2d_bytes_per_step": 8 * samples_per_step, "d2h_bytes_per_step": d2h,
-                    "api": "fosphor_cu_process_host x384 + fosphor_cu_finish (page-locked host pre-overlapped stream)"},
+            "e2e": e2e,
             "one_stream": one,
-            "overlap_in_engine": {"value": value_hop, "e2e": e2e_raw, "unit": "Mcomplex-samples/s",
-                                  "h2d_bytes_per_step": 8 * raw_len,
-                                  "note": "raw stream, hop=N/4 addressing inside the FFT kernel (r=1/4)"},
+            "unfolded": unfolded,
+            "overlap_in_engine": {"value": value_hop, "unit": "Mcomplex-samples/s",
+                                  "note": "raw stream, hop=N/4 addressing inside the FFT kernel (r=1/4), device-resident"},
         }
+        if extras is not None:
+            out["configs"] = extras
         if cpu is not None:
             out["cpu_baseline"] = cpu
         print(json.dumps(out))
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_extras(torch, dev, stream, local, peak, raws):
+    """cfg3, cfg4 (one channel), the cfg5 size sweep and the two stress inputs (constant DC = every
+    hit of a column in one bin: worst-case shared-atomic contention; all zeros = the -inf path),
+    device-resident on one GPU, each with its own fraction of the HBM roofline (SURVEY 8d bytes)."""
+    from gr_fosphor_b200.engine import Fosphor
+
+    def run(name, n, k, ov, b, calls, in_engine, fill=None, steps=6, **kw):
+        hopv = n // ov if in_engine else n
+        spectra = calls * b
+        raw_len = (spectra - 1) * hopv + n
+        bufs = []
+        if fill is not None:
+            x = torch.empty((raw_len, 2), device=dev, dtype=torch.float32)
+            x[:, 0], x[:, 1] = fill
+            bufs = [x, x]
+        elif n == N_FFT and in_engine and raw_len <= raws[0].shape[0]:
+            bufs = raws
+        else:
+            g = torch.Generator(device=dev)
+            g.manual_seed(5)
+            for _ in range(2):
+                x = torch.randn((raw_len, 2), generator=g, device=dev, dtype=torch.float32) * 0.01
+                x[:, 0] += 0.3 * torch.cos(torch.arange(raw_len, device=dev, dtype=torch.float32) * 0.37)
+                bufs.append(x)
+        eng = Fosphor(fft_len=n, n_bins=k, wf_rows=1024, device=local, stream=stream.cuda_stream, **kw)
+        torch.cuda.synchronize()
+        for i in range(3):
+            eng.process_device_multi(bufs[i % 2].data_ptr(), calls, b, hopv)
+        eng.flush()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            eng.process_device_multi(bufs[i % 2].data_ptr(), calls, b, hopv)
+        eng.flush()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        eng.profile(True)
+        for i in range(2):
+            eng.process_device_multi(bufs[i % 2].data_ptr(), calls, b, hopv)
+        prof = eng.profile_read()
+        eng.profile(False)
+        ring = eng.host_feed_stats()["ring_rows"]
+        eng.close()
+        r = 1.0 / ov if in_engine else 1.0
+        gbps = calls * algorithmic_bytes_per_call(n, k, b, r) / ms / 1e6
+        fft_us = prof["fft_ms"] / max(1, prof["fft_launches"]) * 1e3
+        acc_us = (prof["count_ms"] / max(1, prof["count_launches"]) +
+                  prof["update_ms"] / max(1, prof["update_launches"])) * 1e3
+        spl = 2 * spectra / max(1, prof["fft_launches"])
+        res = {"config": name, "fft_len": n, "n_bins": k, "overlap": ov, "batch": b, "calls_per_step": calls,
+               "in_engine_overlap": in_engine, "r": r, "log_power_ring_rows": ring,
+               "Msamples_per_s": spectra * n / ms / 1e3, "spectra_per_s": spectra / ms * 1e3,
+               "ms_per_step": ms, "algorithmic_GBps": gbps, "frac": gbps / peak,
+               "fft_us_per_launch": fft_us, "accumulate_us_per_launch": acc_us,
+               "fft_kernel_GBps": fft_kernel_bytes(n, spl, r) / (fft_us * 1e-6) / 1e9 if fft_us else None,
+               "fft_kernel_frac": fft_kernel_bytes(n, spl, r) / (fft_us * 1e-6) / 1e9 / peak if fft_us else None}
+        del bufs
+        torch.cuda.empty_cache()
+        return res
+
+    out = []
+    # cfg3: N=4096, 512 bins, overlap 8, tau=0.95 -> t0d=20, B=256
+    out.append(run("cfg3 persistence stress", 4096, 512, 8, 256, 256, True, t0d=20.0))
+    # cfg4 shape on one GPU (one channel): N=16384, 1024 bins, B=1024, pre-overlapped (r=1)
+    out.append(run("cfg4 one channel", 16384, 1024, 1, 1024, 16, False))
+    # cfg5 sweep: K=256, overlap 4, B=1024, about 0.27 G samples per step at every size
+    for n in (512, 1024, 2048, 4096, 8192, 16384):
+        out.append(run("cfg5 sweep N=%d" % n, n, 256, 4, 1024, (1 << 28) // n // 1024, True))
+    # cfg5 stress inputs at N=1024
+    out.append(run("cfg5 stress: constant DC (all hits of a column in one bin)", 1024, 256, 4, 1024, 256, True,
+                   fill=(0.25, 0.1)))
+    out.append(run("cfg5 stress: all zeros (-inf path)", 1024, 256, 4, 1024, 256, True, fill=(0.0, 0.0)))
+    return out
+
+
+def run_e2e(torch, dist, dev, local, world, args, lib_path, FosphorCL, Fosphor, stream):
+    """Host-fed figures.  `value` = the like-for-like arm (see the module docstring); the others are
+    the same frames with page-locked input, with FOSPHOR_B200_HOSTREG=1, and the parameterised
+    engine's own host calls (round-1 arm: K=256, 384 calls + finish from page-locked memory; raw
+    stream with in-engine overlap)."""
+    import signals
+    n, b = N_FFT, BATCH
+    frame_samples = FRAME_CALLS * b * n
+    raw = signals.noise_tones((FRAME_CALLS * b - 1) * (n // OVERLAP) + n, seed=2)
+    frame = signals.overlap_windows(raw, n, OVERLAP, FRAME_CALLS * b)          # pageable numpy, 64 MiB
+    call_len = b * n
+    os.environ["FOSPHOR_CUDA_DEV"] = str(local)
+
+    def bracket(fn, reps, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([el], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        return el
+
+    def dropin_frames(src_ptr, reps, env=None):
+        old = {}
+        for kk, vv in (env or {}).items():
+            old[kk] = os.environ.get(kk)
+            os.environ[kk] = vv
+        try:
+            eng = FosphorCL(lib_path)
+        finally:
+            for kk, vv in old.items():
+                if vv is None:
+                    os.environ.pop(kk, None)
+                else:
+                    os.environ[kk] = vv
+
+        def one_frame():
+            for c in range(FRAME_CALLS):
+                rc = eng.process_raw(src_ptr + 8 * c * call_len, call_len)
+                assert rc == 0, rc
+            assert eng.finish() == 1
+        el = bracket(one_frame, reps, 5)
+        eng.release()
+        return world * reps * frame_samples / el / 1e6, el / reps * 1e3
+
+    frames = args.e2e_frames
+    v_page, ms_frame = dropin_frames(frame.ctypes.data, frames)
+    v_reg, _ = dropin_frames(frame.ctypes.data, frames // 2, env={"FOSPHOR_B200_HOSTREG": "1"})
+    pinned = torch.from_numpy(frame.view(np.float32)).pin_memory()
+    v_pin, _ = dropin_frames(pinned.data_ptr(), frames // 2)
+    one_thread, _ = dropin_frames(frame.ctypes.data, max(8, frames // 8), env={"FOSPHOR_B200_COPY_THREADS": "1"})
+
+    # the parameterised engine from page-locked memory: 48 calls of K=256 + finish, and the raw stream
+    k, calls = N_BINS, 48
+    eng = Fosphor(fft_len=n, n_bins=k, wf_rows=WF_ROWS, device=local, stream=stream.cuda_stream)
+    hop = n // OVERLAP
+    raw2 = signals.noise_tones((calls * b - 1) * hop + n, seed=3)
+    h_raw = torch.from_numpy(raw2.view(np.float32)).pin_memory()
+    r_wf = torch.empty((WF_ROWS, n), dtype=torch.float32).pin_memory()
+    r_hist = torch.empty((k, n), dtype=torch.float32).pin_memory()
+    r_spec = torch.empty((2, n, 2), dtype=torch.float32).pin_memory()
+
+    def raw_step():
+        eng.process_host_raw_ptr(h_raw.data_ptr(), calls, b, hop)
+        assert eng.finish_into(r_wf.data_ptr(), r_hist.data_ptr(), r_spec.data_ptr()) == 1
+    el = bracket(raw_step, 20, 3)
+    v_raw = world * 20 * calls * b * n / el / 1e6
+    eng.close()
+
+    return {"value": v_page, "unit": "Mcomplex-samples/s",
+            "h2d_bytes_per_step": 8 * frame_samples, "d2h_bytes_per_step": 4 * (WF_ROWS * n + REF_BINS * n + 4 * n),
+            "step": "one sink frame: 8 x fosphor_cl_process(1024 spectra) + fosphor_cl_finish; %d frames timed" % frames,
+            "ms_per_frame": ms_frame,
+            "api": "the drop-in's fosphor_cl_* symbols (lib/fosphor/cl.h:22-32), PAGEABLE numpy input staged by the "
+                   "engine's copy threads, 128 bins, 1024 rows - the same calls, geometry and memory type as "
+                   "--impl reference",
+            "pcie_GBps": v_page * 8e6 / 1e9 / world,
+            "variants": {
+                "dropin_pageable_default": v_page,
+                "dropin_pageable_one_copy_thread": one_thread,
+                "dropin_pageable_hostreg": v_reg,
+                "dropin_page_locked_input": v_pin,
+                "engine_raw_stream_in_engine_overlap": v_raw,
+                "notes": "hostreg: FOSPHOR_B200_HOSTREG=1 page-locks the caller's buffer on first sight (opt-in, "
+                         "for long-lived sample rings like the sink's FIFO); page_locked: cudaHostAlloc'ed source "
+                         "(the pinned FIFO of SURVEY 8f#2); raw stream: fosphor_cu_process_host_raw, hop=N/4, each "
+                         "raw sample crosses PCIe once (x4 fewer bytes per FFT sample)"}}
 
 
 def run_reference(args):
@@ -433,7 +649,7 @@ def run_reference(args):
     if rank != 0:
         return
     import signals
-    n, b, calls = N_FFT, BATCH, REF_CALLS_PER_STEP
+    n, b, calls = N_FFT, BATCH, FRAME_CALLS
     raw = signals.noise_tones((calls * b - 1) * (n // OVERLAP) + n, seed=2)
     x = signals.overlap_windows(raw, n, OVERLAP, calls * b).reshape(calls, b * n)
     samples_per_step = calls * b * n
@@ -466,32 +682,35 @@ def run_reference(args):
         step()
     el = time.perf_counter() - t0
     value = args.steps * samples_per_step / el / 1e6
-    sample = ("%d steps of 8 calls x 1024 spectra, %s" %
+    sample = ("%d steps of 8 calls x 1024 spectra + finish, %s" %
               (args.steps, "reference OpenCL kernels on the box's B200 via NVIDIA OpenCL (no CPU OpenCL platform exists), 128 bins"
                if kind == "reference" else "CPU oracle port, f32 FFT, all host threads, 128 bins"))
     out = {"impl": "reference", "metric": "Mcomplex-samples/sec through FFT+histogram at N=1024",
            "value": value, "unit": "Mcomplex-samples/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "cfg2: N=1024, overlap=4 (pre-overlapped stream), B=1024 spectra/call, "
-                                  "step = 8 calls + finish; reference fixed at 128 bins"},
+           "config": CONFIG,
+           "details": {"step": "one sink frame (config.e2e_frame); at N>1 rank 0 alone runs (one GPU busy)"},
            "cpu_baseline": {"value": value, "unit": "Mcomplex-samples/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "Mcomplex-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if kind == "reference" and not args.no_cpu:
         # the box has no CPU OpenCL platform, so the reference's own kernels ran on the GPU; for a
         # host-cores figure next to it: the oracle port (same arithmetic, OpenMP), bounded sample
-        out["cpu_port"] = cpu_baseline_port(seconds_budget=8.0)
+        out["cpu_port"] = cpu_baseline_port(seconds_budget=8.0, n_bins=REF_BINS)
     print(json.dumps(out))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--passes", type=int, default=50, help="passes (1 s of signal = 384 calls each) per step")
+    ap.add_argument("--e2e-frames", type=int, default=400, help="sink frames timed by the e2e arm")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--wf-rows", type=int, default=WF_ROWS, help="device waterfall ring rows (power of two)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg3 / cfg4 / cfg5 device-resident figures")
+    ap.add_argument("--wf-rows", type=int, default=WF_ROWS, help="waterfall rows (power of two)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

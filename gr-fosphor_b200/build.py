@@ -6,8 +6,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfosphor_b200.so")
-SOURCES = ["engine.cu", "dropin.cu", "../host/pinned_fifo.cc", "../host/window.cc"]
-HEADERS = ["fft_regs.cuh", "fft_power.cuh", "accumulate.cuh", "../host/pinned_fifo.h"]
+SOURCES = ["engine.cu", "dropin.cu", "../host/pinned_fifo.cc", "../host/window.cc", "../host/copy_pool.cc"]
+HEADERS = ["fft_regs.cuh", "fft_power.cuh", "accumulate.cuh", "../host/pinned_fifo.h", "../host/copy_pool.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1046,6 +1046,18 @@ __global__ void fill_kernel(float *p, size_t n, float v)
 		p[i] = v;
 }
 
+/* The last `cnt` rows of the engine's log-power scratch ring -> the user-visible waterfall ring
+ * (display.cl:141-146 writes them there directly; here only when somebody looks, engine.cu: publish). */
+__global__ void publish_rows_kernel(const float4 *__restrict__ ring, float4 *__restrict__ wf, int n4, int cnt,
+                                    int src0, int src_mask, int dst0, int dst_mask)
+{
+	const size_t total = (size_t)cnt * n4;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const int r = (int)(i / n4), c = (int)(i - (size_t)r * n4);
+		wf[(size_t)((dst0 + r) & dst_mask) * n4 + c] = __ldcs(&ring[(size_t)((src0 + r) & src_mask) * n4 + c]);
+	}
+}
+
 /* max-hold trace (y values, display order) for the multi-GPU reduce */
 __global__ void export_maxhold_kernel(const float2 *spectrum, int n, float *out)
 {

@@ -12,6 +12,7 @@
 #include <cerrno>
 #include <new>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/fosphor_b200.h"
 #include "../../include/fosphor_private_abi.h"
@@ -42,6 +43,11 @@ int fosphor_cl_init(struct fosphor *self)
 
 	fosphor_cu_params p;
 	fosphor_cu_default_params(&p);             /* N=1024, 128 bins, 1024 rows, 16/1024 */
+	p.scratch_rows = -1;                       /* one call per launch pair: the waterfall is the ring */
+	/* cl.c:279 lets FOSPHOR_CL_DEV=<platform>:<device> pick the OpenCL device; here
+	 * FOSPHOR_CUDA_DEV=<ordinal> picks the CUDA device (default: the current one) */
+	if (const char *dev = getenv("FOSPHOR_CUDA_DEV"))
+		p.device = atoi(dev);
 	int rc = fosphor_cu_create(&s->eng, &p);
 	if (rc) {
 		fprintf(stderr, "[!] No suitable CUDA device / engine init failed (%d)\n", rc);
@@ -85,7 +91,10 @@ int fosphor_cl_process(struct fosphor *self, void *samples, int len)
 int fosphor_cl_finish(struct fosphor *self)
 {
 	DropinState *s = st(self);
-	int rc = fosphor_cu_finish(s->eng, self->img_waterfall, self->img_histogram, self->buf_spectrum);
+	/* self->img_* are the caller's persistent images (fosphor.c:52-54): only the waterfall rows
+	 * written since the last finish travel (cl.c:1012-1021 re-reads the whole ring every frame) */
+	int rc = fosphor_cu_finish_new_rows(s->eng, self->img_waterfall, self->img_histogram, self->buf_spectrum,
+	                                    nullptr, nullptr);
 	return rc < 0 ? -EIO : rc;                 /* cl.c:1057,1060 */
 }
 

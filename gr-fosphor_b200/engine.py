@@ -17,7 +17,8 @@ class Params(C.Structure):
     _fields_ = [("fft_len", C.c_int), ("n_bins", C.c_int), ("wf_rows", C.c_int),
                 ("batch_mult", C.c_int), ("batch_max", C.c_int),
                 ("histo_t0r", C.c_float), ("histo_t0d", C.c_float), ("live_alpha", C.c_float),
-                ("maxhold_keep", C.c_float), ("maxhold_mix", C.c_float), ("device", C.c_int)]
+                ("maxhold_keep", C.c_float), ("maxhold_mix", C.c_float), ("device", C.c_int),
+                ("scratch_rows", C.c_int)]
 
 
 _lib = None
@@ -47,6 +48,14 @@ def load_library(path=None):
     L.fosphor_cu_process_device_multi.argtypes = [vp, vp, C.c_int, C.c_int, ll]
     L.fosphor_cu_process_host_raw.argtypes = [vp, vp, C.c_int, C.c_int, ll]
     L.fosphor_cu_finish.argtypes = [vp, vp, vp, vp]
+    L.fosphor_cu_finish_new_rows.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.fosphor_cu_default_window.argtypes = [C.c_int, vp]
+    L.fosphor_cu_default_window.restype = None
+    L.fosphor_cu_power_range.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.fosphor_cu_power_range.restype = None
+    L.fosphor_cu_export_maxhold_on.argtypes = [vp, vp, vp]
+    L.fosphor_cu_host_feed_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong),
+                                             C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.fosphor_cu_sync.argtypes = [vp]
     L.fosphor_cu_flush.argtypes = [vp]
     L.fosphor_cu_two_stream_chunks.argtypes = [vp]
@@ -70,19 +79,17 @@ def load_library(path=None):
 
 
 def default_window(n):
-    """lib/fosphor/fosphor.c:113-118 generalised to N (f32 arithmetic)."""
-    f = np.float32
-    i = np.arange(n, dtype=np.float32)
-    arg = (f(2.0) * f(3.141592) * i) / f(n)
-    return ((f(0.54) - f(0.46) * np.cos(arg, dtype=np.float32)) * f(1.855)).astype(np.float32)
+    """lib/fosphor/fosphor.c:113-118 generalised to N: the library's C helper."""
+    w = np.empty(n, np.float32)
+    load_library().fosphor_cu_default_window(n, w.ctypes.data)
+    return w
 
 
 def power_range(n, db_ref, db_per_div):
-    """lib/fosphor/fosphor.c:131-152 -> (scale, offset) f32, with k = log10(N)."""
-    f = np.float32
-    db0 = db_ref - 10 * db_per_div
-    k = f(np.log10(np.float64(n)))   # == C log10f((float)N): correctly rounded for these N
-    return f(f(20.0) / f(db_ref - db0)), f(-(k + f(db0) / f(20.0)))
+    """lib/fosphor/fosphor.c:131-152 -> (scale, offset) f32: the library's C helper."""
+    s, o = C.c_float(), C.c_float()
+    load_library().fosphor_cu_power_range(n, int(db_ref), int(db_per_div), C.byref(s), C.byref(o))
+    return np.float32(s.value), np.float32(o.value)
 
 
 class Fosphor:
@@ -90,7 +97,7 @@ class Fosphor:
 
     def __init__(self, fft_len=1024, n_bins=128, wf_rows=1024, batch_mult=16, batch_max=1024,
                  t0r=16.0, t0d=1024.0, alpha=0.002, device=-1, window=None,
-                 db_ref=0, db_per_div=10, stream=None):
+                 db_ref=0, db_per_div=10, stream=None, scratch_rows=0):
         self.lib = load_library()
         p = Params()
         self.lib.fosphor_cu_default_params(C.byref(p))
@@ -98,6 +105,7 @@ class Fosphor:
         p.batch_mult, p.batch_max = batch_mult, batch_max
         p.histo_t0r, p.histo_t0d, p.live_alpha = t0r, t0d, alpha
         p.device = device
+        p.scratch_rows = scratch_rows
         self.p = p
         self.n, self.k, self.w = fft_len, n_bins, wf_rows
         self.h = C.c_void_p()
@@ -165,6 +173,19 @@ class Fosphor:
         rc = self._chk(self.lib.fosphor_cu_finish(self.h, *ptrs))
         return rc, self._host
 
+    def finish_new_rows(self):
+        """finish() that refreshes only the waterfall rows written since the previous one in the
+        persistent host image; returns (rc, host arrays, first_row, n_rows)."""
+        if not hasattr(self, "_host"):
+            self._host = {"waterfall": np.zeros((self.w, self.n), np.float32),
+                          "histogram": np.zeros((self.k, self.n), np.float32),
+                          "spectrum": np.zeros((2, self.n, 2), np.float32)}
+        r0, nr = C.c_int(), C.c_int()
+        rc = self._chk(self.lib.fosphor_cu_finish_new_rows(
+            self.h, self._host["waterfall"].ctypes.data, self._host["histogram"].ctypes.data,
+            self._host["spectrum"].ctypes.data, C.byref(r0), C.byref(nr)))
+        return rc, self._host, r0.value, nr.value
+
     def finish_into(self, wf_ptr, hist_ptr, spec_ptr):
         """finish() into caller-owned host memory (e.g. page-locked buffers); 0 pointers skip an array."""
         return self._chk(self.lib.fosphor_cu_finish(self.h, C.c_void_p(wf_ptr or None),
@@ -205,6 +226,16 @@ class Fosphor:
 
     def export_maxhold(self, out_dev_ptr):
         return self._chk(self.lib.fosphor_cu_export_maxhold(self.h, C.c_void_p(out_dev_ptr)))
+
+    def export_maxhold_on(self, out_dev_ptr, side_stream):
+        """export on a caller stream (e.g. the NCCL stream) without joining the engine's streams"""
+        return self._chk(self.lib.fosphor_cu_export_maxhold_on(self.h, C.c_void_p(out_dev_ptr),
+                                                                C.c_void_p(int(side_stream))))
+
+    def host_feed_stats(self):
+        a, b, c, d = C.c_ulonglong(), C.c_ulonglong(), C.c_int(), C.c_int()
+        self._chk(self.lib.fosphor_cu_host_feed_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"staged_calls": a.value, "direct_calls": b.value, "copy_threads": c.value, "ring_rows": d.value}
 
     def debug_fft(self, in_dev_ptr, n_spectra, hop, out_dev_ptr):
         return self._chk(self.lib.fosphor_cu_debug_fft(

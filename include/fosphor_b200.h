@@ -65,9 +65,11 @@ void fosphor_cl_set_histogram_range(struct fosphor *self, float scale, float off
 /* 2. Parameterised engine                                                    */
 /* ------------------------------------------------------------------------ */
 
+#define FOSPHOR_CU_MAX_BINS 1024
+
 struct fosphor_cu_params {
 	int fft_len;        /* N: 512, 1024, 2048, 4096, 8192 or 16384 (ref: private.h:21-22) */
-	int n_bins;         /* K power bins, 2..4096              (ref: 128, display.cl:96)    */
+	int n_bins;         /* K power bins, 2..FOSPHOR_CU_MAX_BINS (ref: 128, display.cl:96)  */
 	int wf_rows;        /* W waterfall ring rows, power of two >= batch_max (ref: 1024)   */
 	int batch_mult;     /* spectra per call must be a multiple of this (ref: 16)          */
 	int batch_max;      /* and at most this                              (ref: 1024)      */
@@ -77,6 +79,13 @@ struct fosphor_cu_params {
 	float maxhold_keep; /* ref 0.999, display.cl:303 */
 	float maxhold_mix;  /* ref 0.001, display.cl:303 */
 	int device;         /* CUDA device ordinal, -1 = current device */
+	int scratch_rows;   /* The engine's internal log-power ring, which decides how many calls
+	                     * fosphor_cu_process_device_multi / _host_raw fold into one launch pair
+	                     * (independent of wf_rows, which is only what the display shows):
+	                     * 0 = automatic (grown on demand up to 1 GiB, an eighth of the free
+	                     * device memory at most), > 0 = at most this many rows (rounded up to
+	                     * a power of two), < 0 = never (the waterfall itself is the ring: one
+	                     * launch pair per wf_rows rows, as in round 1). */
 };
 
 struct fosphor_cu; /* opaque */
@@ -95,9 +104,22 @@ int fosphor_cu_load_fft_window(struct fosphor_cu *e, const float *win_host);
 /* Stores scale * n_bins and offset (cl.c:1081-1089). */
 int fosphor_cu_set_histogram_range(struct fosphor_cu *e, float scale, float offset);
 
+/* What the caller of the boundary computes for the reference's fixed N = 1024, for any N
+ * (SURVEY.md 8a T2): the default window of fosphor.c:108-121 (periodic Hamming x 1.855, pi
+ * truncated to 3.141592f) and the power range -> (scale, offset) math of fosphor.c:131-152
+ * (offset = -(log10f(N) + db0/20), scale = 20/(db1 - db0), db0 = db_ref - 10 db_per_div). */
+void fosphor_cu_default_window(int fft_len, float *win_out);
+void fosphor_cu_power_range(int fft_len, int db_ref, int db_per_div, float *scale, float *offset);
+
 /* One reference-style call on HOST samples: len complex samples = n_spectra
- * pre-overlapped windows (cl.c:870-968).  Stages through pinned memory; the
- * source buffer is free when the call returns. */
+ * pre-overlapped windows (cl.c:870-968).  The source buffer is free when the call
+ * returns (base_sink_c_impl.cc:170-174).  Page-locked sources are DMA'd in place;
+ * pageable ones (the unmodified sink's FIFO, lib/fifo.cc:17-21) are staged by a
+ * few copy threads, piece by piece, the DMA of a piece overlapping the copy of the
+ * next (FOSPHOR_B200_COPY_THREADS, default min(8, cores/2)).  With
+ * FOSPHOR_B200_HOSTREG=1 the engine instead page-locks the caller's buffer where it
+ * lies the first time it sees it - only for callers whose sample memory outlives the
+ * engine, as the sink's FIFO does. */
 int fosphor_cu_process_host(struct fosphor_cu *e, const void *samples_host, int len);
 
 /* One call on DEVICE-resident samples.  Spectrum s is read at
@@ -125,6 +147,13 @@ int fosphor_cu_process_host_raw(struct fosphor_cu *e, const void *raw_host,
  * spectrum float2 live[N] + float2 max[N]; 0 = nothing new. Synchronises. */
 int fosphor_cu_finish(struct fosphor_cu *e, float *waterfall_host,
                       float *histogram_host, float *spectrum_host);
+/* Same, but only the waterfall rows written since the previous finish are copied (all of them the
+ * first time and after >= wf_rows new rows): right when waterfall_host is the caller's persistent
+ * image of the ring, as self->img_waterfall is (fosphor.c:52, cl.c:1012-1021 re-reads all 4 MiB
+ * per frame).  first_row / n_rows (may be NULL) report the ring rows refreshed (n_rows may wrap). */
+int fosphor_cu_finish_new_rows(struct fosphor_cu *e, float *waterfall_host,
+                               float *histogram_host, float *spectrum_host,
+                               int *first_row, int *n_rows);
 /* Wait for all enqueued work (no copies). */
 int fosphor_cu_sync(struct fosphor_cu *e);
 /* Order the engine's stream after all process work enqueued so far, without waiting on the host.
@@ -148,6 +177,13 @@ float *fosphor_cu_device_spectrum(struct fosphor_cu *e);   /* [2][N][2]         
  * input to the multi-GPU ncclMax reduce.  Asynchronous on the engine stream. */
 int fosphor_cu_export_maxhold(struct fosphor_cu *e, float *out_dev);
 
+/* Same on a stream of the caller's (cudaStream_t as void*), e.g. the one its NCCL all-reduce runs
+ * on: that stream is ordered after the engine's last accumulate launch, the engine's own stream is
+ * NOT - the next process call's FFT still overlaps that launch (export_maxhold would join the two
+ * streams and drain the pipeline once per reduction).  The next accumulate launch waits for this
+ * read.  Work the caller enqueues on side_stream afterwards sees the exported trace. */
+int fosphor_cu_export_maxhold_on(struct fosphor_cu *e, float *out_dev, void *side_stream);
+
 /* Test hook: windowed forward FFT only, cf32 [n_spectra][N] out (device). */
 int fosphor_cu_debug_fft(struct fosphor_cu *e, const void *samples_dev,
                          int n_spectra, long long hop, void *out_dev);
@@ -160,6 +196,10 @@ int fosphor_cu_debug_fft(struct fosphor_cu *e, const void *samples_dev,
 int fosphor_cu_profile(struct fosphor_cu *e, int enable);
 int fosphor_cu_profile_read(struct fosphor_cu *e, double *ms, unsigned long long *launches);
 
+/* Diagnostics of the host-fed path: process calls whose samples were staged by the copy threads /
+ * DMA'd straight from page-locked caller memory, copy threads running, rows of the log-power ring. */
+int fosphor_cu_host_feed_stats(const struct fosphor_cu *e, unsigned long long *staged_calls,
+                               unsigned long long *direct_calls, int *copy_threads, int *ring_rows);
 /* Number of kernel launches issued by this engine so far. */
 unsigned long long fosphor_cu_launch_count(const struct fosphor_cu *e);
 const char *fosphor_cu_last_error(const struct fosphor_cu *e);

@@ -289,8 +289,12 @@ map_bin(float x, int k)
 	return (int)r;
 }
 
+/* pwr_in == NULL: log-power from the complex spectra of this call (the path);
+ * pwr_in != NULL: [batch][N] log-power rows given by the caller - the same
+ * display arithmetic on somebody else's waterfall rows (stage-wise parity:
+ * fosphor_oracle_process_pwr) */
 static void
-display(struct fosphor_oracle *o, int batch)
+display(struct fosphor_oracle *o, int batch, const float *pwr_in)
 {
 	const int n = o->p.fft_len, kb = o->p.n_bins, wmask = o->p.wf_rows - 1;
 	const float alpha = o->p.live_alpha;
@@ -320,7 +324,7 @@ display(struct fosphor_oracle *o, int batch)
 
 		for (int sp = 0; sp < batch; sp++) {
 			const float *x = &o->fft_out[2 * ((size_t)sp * n + f)];
-			float pwr = log_power(o, x[0], x[1]);
+			float pwr = pwr_in ? pwr_in[(size_t)sp * n + f] : log_power(o, x[0], x[1]);
 			r = sp % ROWS;
 			max_buf[r] = fmaxf(max_buf[r], pwr);                 /* :139 */
 			o->waterfall[(size_t)((o->wf_pos + sp) & wmask) * n + f] = pwr; /* :141-146 */
@@ -401,9 +405,25 @@ process_common(struct fosphor_oracle *o, const float *src, int n_spectra, int ho
 		clear_buffers(o);
 
 	if (n_spectra > 0)
-		display(o, n_spectra);
+		display(o, n_spectra, NULL);
 	o->last_batch = n_spectra;
 
+	o->wf_pos = (o->wf_pos + n_spectra) & (o->p.wf_rows - 1); /* cl.c:954 */
+	o->state = ST_PENDING;
+	return 0;
+}
+
+int
+fosphor_oracle_process_pwr(struct fosphor_oracle *o, const float *pwr_rows, int n_spectra)
+{
+	/* cl.c:881-886, then display.cl:141-310 on the given rows */
+	if (n_spectra < 0 || (n_spectra % o->p.batch_mult) || n_spectra > o->p.batch_max)
+		return -EINVAL;
+	if (o->state == ST_BOOTING) /* cl.c:930-934 */
+		clear_buffers(o);
+	if (n_spectra > 0)
+		display(o, n_spectra, pwr_rows);
+	o->last_batch = n_spectra;
 	o->wf_pos = (o->wf_pos + n_spectra) & (o->p.wf_rows - 1); /* cl.c:954 */
 	o->state = ST_PENDING;
 	return 0;

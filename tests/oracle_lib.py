@@ -43,6 +43,7 @@ def lib():
         L.fosphor_oracle_set_histogram_range.argtypes = [vp, C.c_float, C.c_float]
         L.fosphor_oracle_process.argtypes = [vp, vp, C.c_int]
         L.fosphor_oracle_process_hop.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.fosphor_oracle_process_pwr.argtypes = [vp, vp, C.c_int]
         L.fosphor_oracle_finish.argtypes = [vp]
         L.fosphor_oracle_get_waterfall_position.argtypes = [vp]
         for n in ("waterfall", "histogram", "spectrum", "last_fft", "last_hits"):
@@ -104,6 +105,12 @@ class Oracle:
         x = np.ascontiguousarray(raw, np.complex64)
         assert (n_spectra - 1) * hop + self.n <= x.size or n_spectra == 0
         return lib().fosphor_oracle_process_hop(self.h, x.ctypes.data, n_spectra, hop)
+
+    def process_pwr(self, rows):
+        """one call on given log-power rows [B][N] (display stage only)"""
+        r = np.ascontiguousarray(rows, np.float32)
+        assert r.ndim == 2 and r.shape[1] == self.n
+        return lib().fosphor_oracle_process_pwr(self.h, r.ctypes.data, r.shape[0])
 
     def finish(self):
         return lib().fosphor_oracle_finish(self.h)

@@ -114,6 +114,33 @@ def test_c99_caller_builds_against_the_headers_and_fails_loudly_without_a_gpu(tm
         assert "-EIO" in rc.stderr
 
 
+def test_reference_fosphor_c_links_against_the_dropin():
+    """oracle/ref_link: the reference's UNMODIFIED lib/fosphor/fosphor.c (sole caller of the
+    boundary) links against libfosphor_b200.so with --no-undefined, every fosphor_cl_* symbol
+    resolved by it; without a GPU its fosphor_init() fails loudly (NULL) through the reference's own
+    error path (fosphor.c:69-74: release after a failed cl init)."""
+    import subprocess
+    import torch
+    so = os.path.join(ROOT, "oracle", "_ref", "libfosphor_facade_b200.so")
+    if os.path.isdir("/root/reference/lib/fosphor"):
+        from gr_fosphor_b200 import build
+        build.build()
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "ref_link"), "-s"])
+    if not os.path.exists(so):
+        pytest.skip("facade not built (no reference tree here)")
+    und = subprocess.check_output(["nm", "-D", "--undefined-only", so]).decode()
+    needed = sorted(set(re.findall(r"\b(fosphor_cl_[a-z_]+)", und)))
+    assert needed == ["fosphor_cl_finish", "fosphor_cl_get_waterfall_position", "fosphor_cl_init",
+                      "fosphor_cl_load_fft_window", "fosphor_cl_process", "fosphor_cl_release",
+                      "fosphor_cl_set_histogram_range"]
+    ldd = subprocess.check_output(["ldd", so]).decode()
+    assert "libfosphor_b200.so" in ldd and "not found" not in ldd.split("libfosphor_b200.so")[1].splitlines()[0]
+    if not torch.cuda.is_available():
+        import facade_lib
+        with pytest.raises(RuntimeError):
+            facade_lib.FosphorFacade()
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "gr-fosphor_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -30,6 +30,20 @@ def test_dropin_matches_reference_golden(name):
     eng.release()
 
 
+@pytest.mark.parametrize("name", ["cfg1", "sequence", "frame8", "bh_range", "einval"])
+def test_reference_fosphor_c_over_the_dropin_matches_golden(name):
+    """Link-level drop-in proof: the reference's unmodified fosphor.c (fosphor_init / process / draw,
+    fosphor.h:26-37) linked against libfosphor_b200.so - oracle/ref_link - replays the golden
+    cases; the img_* buffers fosphor.c owns (fosphor.c:52-54) must match what the real reference
+    produced, fosphor_gl_refresh() must be requested exactly when the reference's finish said so."""
+    import facade_lib
+    if not os.path.exists(facade_lib.FACADE_SO):
+        pytest.skip("oracle/_ref/libfosphor_facade_b200.so not built")
+    eng = facade_lib.FosphorFacade()
+    golden_check.check_case(name, eng)
+    eng.release()
+
+
 def test_dropin_side_by_side_with_live_reference():
     if not os.path.exists(REF_SO):
         pytest.skip("oracle/_ref/libfosphor_ref.so not built")
@@ -49,9 +63,10 @@ def test_dropin_side_by_side_with_live_reference():
             spectra += st[1].size // 1024
             continue
         assert ra["wf_pos"] == rb["wf_pos"]
-        parity.check_waterfall(rb["waterfall"], ra["waterfall"])
-        parity.check_histogram(rb["histogram"], ra["histogram"], hits_in_play=max(1, spectra) * 1024)
-        parity.check_spectrum(rb["spectrum"], ra["spectrum"], wf_ref=ra["waterfall"])
+        import oracle_lib
+        sc, of = oracle_lib.power_range(1024, 0, 10)
+        parity.check_end_to_end(rb, ra, np.arange(min(1024, max(1, spectra))), max(1, spectra) * 1024,
+                                np.float32(sc) * np.float32(128), of)
     ref.release()
     mine.release()
 
@@ -98,8 +113,8 @@ def test_pinned_fifo_feeds_the_dropin_without_staging():
         assert orc.process(x[pos:pos + n]) == 0
         pos += n
     assert eng.finish() == 1 and orc.finish() == 1
-    parity.check_waterfall(eng.img_waterfall, orc.waterfall)
-    parity.check_histogram(eng.img_histogram, orc.histogram, hits_in_play=(256 + 1024 + 64) * 1024)
-    parity.check_spectrum(eng.buf_spectrum, orc.spectrum, wf_ref=orc.waterfall)
+    sc, of = oracle_lib.power_range(1024, 0, 10)
+    host = {"waterfall": eng.img_waterfall, "histogram": eng.img_histogram, "spectrum": eng.buf_spectrum}
+    parity.check_end_to_end(host, orc, np.arange(1024), (256 + 1024 + 64) * 1024, np.float32(sc) * np.float32(128), of)
     eng.release()
     L.fosphor_fifo_destroy(f)
