@@ -5,12 +5,23 @@
  *     gr::fft::window::build(d_fft_window, 1024, 6.76)      lib/base_sink_c_impl.cc:251-255
  * for the seven types its GRC block offers (grc/fosphor_glfw_sink_c.block.yml:5-11).
  * gr-fft (>= 3.9, CMakeLists.txt:34) is a third-party dependency that is not
- * vendored in the reference tree and not installed here, so its coefficients
- * cannot be pinned; this restates the published definitions it implements
- * (symmetric windows over ntaps-1 intervals, generalised cosine sums, Kaiser
- * through the zeroth-order modified Bessel function).  The engine itself takes
- * the window as a plain float array, so parity of the hot path never depends
- * on this file.
+ * vendored in the reference tree and not installed here (parity unpinned by
+ * the reference: it has no window tests, and gr-fft cannot be run here); this
+ * restates the published definitions gr-fft implements:
+ *   - CONVENTION: every window is SYMMETRIC over ntaps - 1 intervals
+ *     (w[i] = f(i / (ntaps - 1)), w[0] == w[ntaps-1]), not the periodic /
+ *     "fftbins" form.  (The reference's own DEFAULT window, fosphor.c:108-121,
+ *     is the periodic Hamming x 1.855 - that one is fosphor_cu_default_window.)
+ *   - generalised cosine sums  w[i] = sum_k (-1)^k c_k cos(2 pi k i / (ntaps-1))
+ *     with the coefficient sets named at each case below;
+ *   - flat-top = the 5-term HP / SRS set {1, 1.93, 1.29, 0.388, 0.028} / 4.63867
+ *     (peak 4.636 / 4.63867 = 0.99942; NOT the ISO 18431-2 / Matlab / scipy set
+ *     0.21557895, 0.41663158, ... - the two differ by up to 1.6e-3);
+ *   - Kaiser through the zeroth-order modified Bessel function I0.
+ * tests/test_window.py pins every type against these definitions evaluated in
+ * double, and against scipy's symmetric windows where the sets coincide.  The
+ * engine itself takes the window as a plain float array, so parity of the hot
+ * path never depends on this file.
  */
 #include <cmath>
 
