@@ -40,9 +40,8 @@ constexpr size_t CNT_BUDGET = (size_t)1 << 30;   /* bytes of u16 hit-count slice
 constexpr int N_CHUNK_EV = 64;   /* chunks in flight tracked by the two-stream schedule */
 constexpr size_t UPD_SMEM_MAX = 96 * 1024;   /* dynamic shared memory of update_kernel */
 constexpr size_t UPD_LUT_SMEM_MAX = 64 * 1024;   /* ... of which the (d, e) table: batches up to 8191 rows */
-constexpr int MAX_STAGE_SLOTS = 4;               /* host-sample staging slots (page-locked + device) */
+constexpr int MAX_STAGE_SLOTS = 8;               /* host-sample staging slots (page-locked + device) */
 constexpr size_t STAGE_SLOT_SMALL = (size_t)32 << 20;   /* slots up to this size: 4 of them, larger: 2 */
-constexpr size_t STAGE_PIECE = (size_t)2 << 20;  /* pageable sources are staged and DMA'd in pieces of about this size */
 constexpr size_t SCRATCH_BUDGET = (size_t)1 << 30;   /* automatic log-power scratch ring: at most this many bytes ... */
 constexpr int OUT_CHUNKS = 16;                   /* result read-back: D2H / copy-out pipeline depth */
 constexpr size_t HOSTREG_BUDGET = (size_t)256 << 20; /* caller memory page-locked on the fly (opt-in), at most */
@@ -64,12 +63,20 @@ struct Tuning {
 	int acc_sub_max = 64;      /* ACC_SUB: rows per unrolled body (16 | 64) */
 	int chunk_calls = 0;       /* CHUNK_CALLS: cap on the calls folded per launch (0 = ring) */
 	int count_variant = 1;     /* COUNT_VARIANT: 1 TMA-staged count kernel, 0 plain (split path) */
-	int fft_variant = 2;       /* FFT_VARIANT: 0 plain, 1 TMA stream, 2 + twiddles in registers, 3 + CTA streaming */
+	int fft_variant = 2;       /* FFT_VARIANT: 0 plain kernels; 1 TMA stream (N <= 1024); 2 TMA stream with twiddles in
+	                            * registers (N <= 1024), half-staged persistent kernel (16384); 3 as 2 + CTA-level streaming
+	                            * for 2048..8192; 4 as 2 but the grouped kernel (warp-local late passes) for 8192 / 16384 */
 	int fft_r64 = 0;           /* FFT_R64: two-pass radix-64 plans for N = 2048 / 4096 */
 	int fft_pf = -1;           /* FFT_PF: L2 prefetch distance of the plain FFT kernel (-1 = resident CTAs) */
 	int fft_ctas_per_sm = 0;   /* FFT_CTAS: CTAs/SM of the persistent FFT kernel (0 = automatic) */
 	int hostreg = 0;           /* HOSTREG: page-lock pageable caller buffers on first sight (see upload_staged) */
 	int copy_threads = 0;      /* COPY_THREADS: staging-copy threads (0 = automatic) */
+	int copy_nt = 0;           /* COPY_NT: non-temporal stores into the staging slots.  Off: with plain stores the
+	                            * slots (4 x 8 MiB) stay in the host's last-level cache and the DMA engine reads them
+	                            * there (calls only: 6.29 vs 5.70 Gsamples/s, tools/e2e_probe.py) */
+	int stage_piece_kb = 4096; /* STAGE_PIECE_KB: pageable sources are staged and DMA'd in pieces of about this size
+	                            * (1 / 2 / 4 / 8 MiB: 4.88 / 5.15 / 5.30 / 5.31 Gsamples/s with a finish per frame) */
+	int stage_slots = 0;       /* STAGE_SLOTS: staging slots (0 = 4, or 2 when a slot is larger than 32 MiB) */
 };
 
 int env_int(const char *name, int dflt)
@@ -93,7 +100,7 @@ Tuning tuning_from_env()
 	if (t.acc_group != 1 && t.acc_group != 2 && t.acc_group != 4) t.acc_group = 0;
 	t.acc_mode = env_int("ACC", t.acc_mode);
 	t.acc_cols = env_int("ACC_COLS", 0);
-	if (t.acc_cols != 4 && t.acc_cols != 8) t.acc_cols = 0;
+	if (t.acc_cols != 4 && t.acc_cols != 8 && t.acc_cols != 16 && t.acc_cols != 32) t.acc_cols = 0;
 	{
 		const int b = env_int("ACC_BOX", t.acc_box_max);
 		t.acc_box_max = b >= 256 ? 256 : (b >= 64 ? 64 : (b >= 16 ? 16 : 0));
@@ -107,6 +114,11 @@ Tuning tuning_from_env()
 	t.fft_ctas_per_sm = env_int("FFT_CTAS", t.fft_ctas_per_sm);
 	t.hostreg = env_int("HOSTREG", t.hostreg);
 	t.copy_threads = env_int("COPY_THREADS", t.copy_threads);
+	t.copy_nt = env_int("COPY_NT", t.copy_nt);
+	t.stage_piece_kb = env_int("STAGE_PIECE_KB", t.stage_piece_kb);
+	if (t.stage_piece_kb < 64) t.stage_piece_kb = 64;
+	t.stage_slots = env_int("STAGE_SLOTS", t.stage_slots);
+	if (t.stage_slots < 0 || t.stage_slots > MAX_STAGE_SLOTS) t.stage_slots = 0;
 	return t;
 }
 
@@ -169,6 +181,7 @@ struct fosphor_cu {
 
 	float *d_win = nullptr;
 	float2 *d_tw = nullptr;
+	float2 *d_twg = nullptr;             /* grouped FFT kernel: pass-2 twiddles [group][t][lane] (N = 8192, 16384) */
 	/* The user-visible waterfall (W rows, the reference's 1024, cl.c:430-432) and the ring the
 	 * kernels work in are two things: the FFT kernel writes log-power rows into d_ring (ring_rows
 	 * >= W, a power of two) and the accumulate kernel reads them there.  How many calls one launch
@@ -333,6 +346,39 @@ void build_twiddles(std::vector<float2> &tw)
 	}
 }
 
+/* pass-2 twiddles of the grouped kernel: the very values of the table above, tw[TW1 + t*P2 + k2]
+ * with k2 = R0*lane + g, laid out [g][t][lane] so that a warp reads 256 consecutive bytes */
+template <class P>
+void build_grouped_twiddles(std::vector<float2> &twg)
+{
+	constexpr int R0 = P::R0;
+	twg.resize((size_t)R0 * 32 * 32);
+	for (int g = 0; g < R0; g++)
+		for (int t = 0; t < 32; t++)
+			for (int l = 0; l < 32; l++) {
+				const int k = R0 * l + g;
+				const double a = -2.0 * M_PI * (double)t * (double)k / (double)P::N;
+				twg[((size_t)g * 32 + t) * 32 + l] = make_float2((float)cos(a), (float)sin(a));
+			}
+}
+
+template <class P>
+cudaError_t grouped_launch(fosphor_cu *e, const float2 *in, long long hop, int wf_pos, int n_spectra)
+{
+	using C = GroupedCfg<P>;
+	if (cudaError_t err = ensure_smem(e, fft_power_grouped_kernel<P>, C::SMEM))
+		return err;
+	const int units = (n_spectra + C::SPC - 1) / C::SPC;
+	const int grid = units < e->sm_count ? units : e->sm_count;      /* persistent, one CTA per SM */
+	const bool aligned = ((reinterpret_cast<unsigned long long>(in) & 15ull) == 0) && ((hop & 1) == 0);
+	prof_mark(e, 0, 0);
+	fft_power_grouped_kernel<P><<<grid, C::THREADS, C::SMEM, e->stream>>>(
+		in, hop, e->d_win, e->d_tw, e->d_twg, e->d_ring, wf_pos, e->ring_rows - 1, n_spectra, aligned ? 1 : 0);
+	prof_mark(e, 0, 1);
+	e->launches++;
+	return cudaGetLastError();
+}
+
 template <class P>
 cudaError_t plan_setup(fosphor_cu *e)
 {
@@ -462,6 +508,17 @@ cudaError_t half_stage_launch(fosphor_cu *e, const float2 *in, long long hop, in
 
 cudaError_t launch_fft(fosphor_cu *e, const float2 *in, long long hop, int wf_pos, int n_spectra)
 {
+	/* N = 8192 / 16384, experiment variant 4: warp-local late passes (plain loads: any alignment).
+	 * Measured SLOWER than the kernels it was meant to replace (N = 16384, r = 1: 1126 us per 16384
+	 * spectra vs 926 half-staged / 947 plain; N = 8192: 1093 vs 755 us per 32768): fewer barriers and no
+	 * bank conflicts do not help a kernel whose bound is the l1tex pipe (64 B per sample through
+	 * LDS/STS/LDG either way) - and one phase-locked CTA per SM overlaps less than three plain ones. */
+	if (e->d_twg && e->tn.fft_variant == 4) {
+		if (e->p.fft_len == 16384)
+			return grouped_launch<Plan16384>(e, in, hop, wf_pos, n_spectra);
+		if (e->p.fft_len == 8192)
+			return grouped_launch<Plan8192>(e, in, hop, wf_pos, n_spectra);
+	}
 	/* TMA bulk copies need 16-byte aligned spectra */
 	const bool aligned = ((reinterpret_cast<unsigned long long>(in) & 15ull) == 0) && ((hop & 1) == 0);
 	if (aligned && e->tn.fft_variant != 0) {
@@ -469,7 +526,7 @@ cudaError_t launch_fft(fosphor_cu *e, const float2 *in, long long hop, int wf_po
 			return stream_launch<Plan1024>(e, in, hop, wf_pos, n_spectra);
 		if (e->p.fft_len == 512)
 			return stream_launch<Plan512>(e, in, hop, wf_pos, n_spectra);
-		if (e->p.fft_len == 16384 && e->tn.fft_variant >= 2)
+		if (e->p.fft_len == 16384 && e->tn.fft_variant >= 2 && e->tn.fft_variant != 4)
 			return half_stage_launch<Plan16384>(e, in, hop, wf_pos, n_spectra);
 		/* The CTA-level streaming kernel measured SLOWER than the plain one (N = 4096:
 		 * 101 vs 86 us per 8192 spectra; fewer resident CTAs outweigh the prefetch), so
@@ -768,6 +825,16 @@ size_t fused_smem_need(int n_bins, int batch, int gc)
 	return FusedCfg<COLS, 16, ACC_UW, 256, 1>::smem(n_bins, batch, true, 1);
 }
 
+size_t fused_smem_need_cols(int cols, int n_bins, int batch, int gc)
+{
+	switch (cols) {
+	case 4:  return fused_smem_need<4>(n_bins, batch, gc);
+	case 16: return fused_smem_need<16>(n_bins, batch, gc);
+	case 32: return fused_smem_need<32>(n_bins, batch, gc);
+	default: return fused_smem_need<8>(n_bins, batch, gc);
+	}
+}
+
 /* one launch: count + rise/decay + live + max-hold of n_calls calls */
 int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st, cudaEvent_t count_done,
                             int wf_pos, int n_calls, int batch)
@@ -818,16 +885,24 @@ int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st
 	if (gc == 0)
 		gc = batch <= 256 ? 4 : 1;        /* measured: cfg3 (B = 256) 115 -> 105 us per 32 calls; B = 1024 prefers the deeper stage ring */
 	const size_t smem_max = e->smem_optin;
-	while (gc > 1 && (e->acc_cols == 4 ? fused_smem_need<4>(a.n_bins, batch, gc)
-	                                   : fused_smem_need<8>(a.n_bins, batch, gc)) > smem_max)
+	while (gc > 1 && fused_smem_need_cols(e->acc_cols, a.n_bins, batch, gc) > smem_max)
 		gc >>= 1;
+	if (e->acc_cols > 8) {       /* wide tiles (few CTAs, the rest of the chip stays with the FFT kernel): one variant */
+		gc = 1;
+		if (subr > 16 && e->acc_cols == 32)
+			subr = 16;
+	}
 	/* warp roles (counters / cell updaters): 16 / 8, or 8 / 16 when a call has more cells to update
 	 * than rows to count (ncu of cfg3, B = 256, K = 512: the counter warps spent half their time
 	 * waiting for the updaters to hand the hit tiles back) */
 	int roles = e->tn.acc_roles;
 	if (roles == 0)
 		roles = (gc == 4 && a.n_bins >= batch) ? 2 : 1;
-	if (e->acc_cols == 4)
+	if (e->acc_cols == 32)
+		err = fused_dispatch<32, 16, ACC_UW, 1>(e, a, st, boxr, subr);
+	else if (e->acc_cols == 16)
+		err = fused_dispatch<16, 16, ACC_UW, 1>(e, a, st, boxr, subr);
+	else if (e->acc_cols == 4)
 		err = slim ? fused_dispatch<4, ACC_FW_SLIM, ACC_UW_SLIM>(e, a, st, boxr, subr)
 		    : gc == 4 ? (roles == 2 ? fused_dispatch<4, 8, 16, 4>(e, a, st, boxr, subr)
 		                            : fused_dispatch<4, 16, ACC_UW, 4>(e, a, st, boxr, subr))
@@ -854,8 +929,7 @@ int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st
 bool use_fused(const fosphor_cu *e, int batch)
 {
 	/* the fused CTA must fit: state tile + hit tiles + partials + table + a minimal stage ring */
-	const size_t need = e->acc_cols == 4 ? fused_smem_need<4>(e->p.n_bins, batch, 1)
-	                                     : fused_smem_need<8>(e->p.n_bins, batch, 1);
+	const size_t need = fused_smem_need_cols(e->acc_cols, e->p.n_bins, batch, 1);
 	if (need > e->smem_optin)
 		return false;
 	return e->tn.acc_mode > 0 || (e->tn.acc_mode < 0 && 2 * batch >= e->p.n_bins && (batch % 16) == 0 && e->acc_tmap_ok);
@@ -1087,7 +1161,7 @@ int ensure_staging(fosphor_cu *e)
 		return 0;
 	e->stage_elems = (size_t)e->p.batch_max * e->p.fft_len;
 	const size_t bytes = sizeof(float2) * e->stage_elems;
-	const int want = bytes <= STAGE_SLOT_SMALL ? MAX_STAGE_SLOTS : 2;
+	const int want = e->tn.stage_slots ? e->tn.stage_slots : (bytes <= STAGE_SLOT_SMALL ? 4 : 2);
 	CU_CHECK(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < want; i++) {
 		CU_CHECK(e, cudaMallocHost(&e->h_in[i], bytes));
@@ -1177,11 +1251,12 @@ int upload_staged(fosphor_cu *e, const float2 *src, size_t n_samples, float2 **d
 		e->await_slot = s;
 		e->direct_calls++;
 	} else {
-		copy_pool *pool = bytes >= 2 * STAGE_PIECE ? get_pool(e) : nullptr;
+		const size_t piece = (size_t)e->tn.stage_piece_kb << 10;
+		copy_pool *pool = bytes >= ((size_t)1 << 20) ? get_pool(e) : nullptr;
 		if (pool) {
-			int pieces = (int)((bytes + STAGE_PIECE - 1) / STAGE_PIECE);
+			int pieces = (int)((bytes + piece - 1) / piece);
 			if (pieces > 16) pieces = 16;     /* large-N calls: 16 DMA requests are plenty */
-			pool->start(e->h_in[s], src, bytes, pieces);
+			pool->start(e->h_in[s], src, bytes, pieces, e->tn.copy_nt != 0);
 			char *hp = reinterpret_cast<char *>(e->h_in[s]), *dp = reinterpret_cast<char *>(e->d_in[s]);
 			cudaError_t err = cudaSuccess;
 			for (int p = 0; p < pieces; p++) {
@@ -1331,6 +1406,7 @@ void fosphor_cu_destroy(struct fosphor_cu *e)
 			cudaGetLastError();
 	if (e->d_ring != e->d_wf)
 		cudaFree(e->d_ring);
+	cudaFree(e->d_twg);
 	cudaFree(e->d_win); cudaFree(e->d_tw); cudaFree(e->d_wf); cudaFree(e->d_hist);
 	cudaFree(e->d_spec); cudaFree(e->d_cnt); cudaFree(e->d_part_live);
 	cudaFree(e->d_part_max);
@@ -1487,6 +1563,15 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 			CREATE_CHECK(cta_stream_setup<Plan4096>(e));
 		if (p.fft_len == 8192)
 			CREATE_CHECK(cta_stream_setup<Plan8192>(e));
+		if ((p.fft_len == 8192 || p.fft_len == 16384) && e->tn.fft_variant == 4) {
+			std::vector<float2> twg;
+			if (p.fft_len == 8192)
+				build_grouped_twiddles<Plan8192>(twg);
+			else
+				build_grouped_twiddles<Plan16384>(twg);
+			CREATE_CHECK(cudaMalloc(&e->d_twg, sizeof(float2) * twg.size()));
+			CREATE_CHECK(cudaMemcpy(e->d_twg, twg.data(), sizeof(float2) * twg.size(), cudaMemcpyHostToDevice));
+		}
 	}
 	{
 		/* fused kernel: narrow tiles so that N / cols CTAs fill the chip, and so that the state +

@@ -681,6 +681,167 @@ fft_power_half_stage_kernel(const float2 *__restrict__ in, long long hop,
 	}
 }
 
+/* ------------------------------------------------------------------------ */
+/* Grouped variant for the R0 x 32 x 32 plans (N = R0 * 1024: 8192, 16384)     */
+/* ------------------------------------------------------------------------ */
+/*
+ * After the first (radix-R0) pass a spectrum falls apart into R0 independent 1024-point
+ * problems: in the Stockham numbering used above, pass-1 butterfly i and pass-2 butterfly i'
+ * exchange data only when i == i' (mod R0).  The plain kernel ignores that and runs both
+ * exchanges through CTA-wide barriers (ncu of N = 16384: issue slots 52 % busy, stalls per issue
+ * barrier 0.89 + mio_throttle 1.10 + short_scoreboard 0.72).  Here
+ *   - warp g of a spectrum owns group g (butterflies i = R0*l + g, l = lane) in BOTH late passes,
+ *     so everything between pass 0 and the output is warp-local: __syncwarp instead of four
+ *     block barriers, and the group's 1024 values live in a private region with the classic
+ *     33-stride transpose padding - every access of every pass is conflict free;
+ *   - only pass 0 meets across warps (block barrier 1), and because group g produces exactly
+ *     the outputs X[k], k == g (mod R0), the log-power values are parked as f32 in the group's
+ *     own region and written out by all threads of the spectrum as coalesced 16-byte stores
+ *     (barriers 2 and 3);
+ *   - a CTA is 16 warps = 16 groups = 16/R0 spectra, persistent, one per SM; the inputs of the
+ *     next spectrum are requested (plain coalesced loads of data pulled into L2 one iteration
+ *     earlier) before the copy-out of the current one and land in registers meanwhile.
+ * Same butterflies, same twiddle values, same operation order as fft_power_kernel with the
+ * same plan: bit-identical rows.
+ */
+template <class P>
+struct GroupedCfg {
+	static_assert(P::NPASS == 3 && P::R1 == 32 && P::N == P::R0 * 1024, "R0 x 32 x 32 plans");
+	static constexpr int R0 = P::R0;
+	static constexpr int WARPS = 16;
+	static constexpr int THREADS = WARPS * 32;
+	static constexpr int SPC = WARPS / R0;                  /* spectra per CTA and iteration */
+	static constexpr int TPS = 32 * R0;                     /* threads per spectrum */
+	static constexpr int BF0 = 32 / R0;                     /* pass-0 butterflies per thread */
+	/* float2 per group region: 1024 + 31 of transpose padding, rounded so that consecutive regions
+	 * start two banks apart as f32 arrays (the copy-out reads R0 regions at once) */
+	static constexpr int REGION = 1057;
+	static constexpr size_t SMEM = sizeof(float2) * (size_t)REGION * WARPS;
+	static constexpr int TWG_ELEMS = R0 * 32 * 32;          /* pass-2 twiddles regrouped [g][t][lane] */
+};
+
+template <class P>
+__global__ void __launch_bounds__(GroupedCfg<P>::THREADS, 1)
+fft_power_grouped_kernel(const float2 *__restrict__ in, long long hop,
+                         const float *__restrict__ win, const float2 *__restrict__ tw,
+                         const float2 *__restrict__ twg,
+                         float *__restrict__ wf, int wf_pos, int wf_mask, int n_spectra, int prefetch)
+{
+	using C = GroupedCfg<P>;
+	constexpr int N = P::N, R0 = C::R0, NB0 = P::NB0;
+	static_assert(NB0 == 1024, "pass-0 butterflies per spectrum");
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int q = warp / R0, g = warp % R0;                  /* spectrum slot of this warp, its group */
+	const int ts = g * 32 + lane;                            /* thread within the spectrum */
+	float2 *slot = reinterpret_cast<float2 *>(smem_raw) + (size_t)q * R0 * C::REGION;
+	float2 *mine = slot + (size_t)g * C::REGION;
+	const int stride = gridDim.x * C::SPC;
+	int s = blockIdx.x * C::SPC + q;
+
+	auto slot_barrier = [&]() {                              /* the 32*R0 threads of this spectrum */
+		if constexpr (C::SPC == 1)
+			__syncthreads();
+		else
+			asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(C::TPS) : "memory");
+	};
+
+	float2 v0[C::BF0][R0];
+	auto load_inputs = [&](int sp) {
+		const float2 *x = in + (long long)sp * hop;
+#pragma unroll
+		for (int u = 0; u < C::BF0; u++)
+#pragma unroll
+			for (int t = 0; t < R0; t++)
+				v0[u][t] = __ldcg(&x[ts + u * C::TPS + t * NB0]);
+	};
+
+	if (s < n_spectra)
+		load_inputs(s);
+	for (; s < n_spectra; s += stride) {
+		/* the spectrum after next: into L2 now, so that its loads (issued one iteration from now,
+		 * before the copy-out) find it there */
+		if (prefetch && ts == 0 && s + 2 * stride < n_spectra)
+			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+			             ::"l"(in + (long long)(s + 2 * stride) * hop), "r"((unsigned)(sizeof(float2) * N)) : "memory");
+
+		/* ---- pass 0 (radix R0, no twiddles): registers -> the R0 group regions ---- */
+#pragma unroll
+		for (int u = 0; u < C::BF0; u++) {
+			const int i0 = ts + u * C::TPS;
+#pragma unroll
+			for (int t = 0; t < R0; t++)
+				v0[u][t] = win_mul(v0[u][t], __ldg(&win[i0 + t * NB0]));   /* fft.cl:416-417 */
+			dif<R0>(v0[u]);
+		}
+		slot_barrier();                  /* the copy-out of the previous spectrum has left the regions */
+#pragma unroll
+		for (int u = 0; u < C::BF0; u++) {
+			const int i0 = ts + u * C::TPS;
+			float2 *dst = slot + i0 + (i0 >> 5);
+			static_for<0, R0>([&](auto tc) {
+				constexpr int t = decltype(tc)::value;
+				dst[t * C::REGION] = v0[u][brev<R0>(t)];     /* Stockham position R0*i0 + t: group t, element i0 */
+			});
+		}
+		slot_barrier();
+
+		/* ---- pass 1 (P = R0): butterfly i = R0*lane + g, warp-local ---- */
+		float2 v[32];
+#pragma unroll
+		for (int t = 0; t < 32; t++)
+			v[t] = mine[lane + 33 * t];                      /* element lane + 32 t of the group */
+#pragma unroll
+		for (int t = 1; t < 32; t++)
+			v[t] = cmul(v[t], __ldg(&tw[t * R0 + g]));       /* k = i & (R0-1) = g: one value per warp */
+		dif<32>(v);
+		__syncwarp();
+		static_for<0, 32>([&](auto tc) {
+			constexpr int t = decltype(tc)::value;
+			mine[33 * lane + t] = v[brev<32>(t)];            /* element 32 lane + t */
+		});
+		__syncwarp();
+
+		/* ---- pass 2 (P = 32 R0), last: same butterflies, outputs X[R0 (lane + 32 t) + g] ---- */
+#pragma unroll
+		for (int t = 0; t < 32; t++)
+			v[t] = mine[lane + 33 * t];
+#pragma unroll
+		for (int t = 1; t < 32; t++)
+			v[t] = cmul(v[t], __ldg(&twg[(g * 32 + t) * 32 + lane]));
+		dif<32>(v);
+		__syncwarp();                        /* every lane has its inputs: the region becomes the f32 parking lot */
+		{
+			float *park = reinterpret_cast<float *>(mine);
+			static_for<0, 32>([&](auto tc) {
+				constexpr int t = decltype(tc)::value;
+				park[lane + 32 * t] = log_power(v[brev<32>(t)]);   /* display.cl:136 */
+			});
+		}
+		slot_barrier();
+
+		/* inputs of this slot's next spectrum: in flight during the copy-out */
+		if (s + stride < n_spectra)
+			load_inputs(s + stride);
+
+		/* ---- copy-out: X[k] sits in group k % R0 at k / R0 ---- */
+		{
+			float *row = wf + (size_t)((wf_pos + s) & wf_mask) * N;
+			const float *parked = reinterpret_cast<const float *>(slot);
+#pragma unroll
+			for (int c = 0; c < N / (4 * C::TPS); c++) {
+				const int k = 4 * (ts + c * C::TPS);
+				float4 o;
+				o.x = parked[((k + 0) % R0) * (2 * C::REGION) + (k + 0) / R0];
+				o.y = parked[((k + 1) % R0) * (2 * C::REGION) + (k + 1) / R0];
+				o.z = parked[((k + 2) % R0) * (2 * C::REGION) + (k + 2) / R0];
+				o.w = parked[((k + 3) % R0) * (2 * C::REGION) + (k + 3) / R0];
+				*reinterpret_cast<float4 *>(row + k) = o;    /* display.cl:141-146 */
+			}
+		}
+	}
+}
+
 /* The supported sizes (BASELINE.json configs[4] sweep) */
 using Plan512   = FftPlan<512,   16, 32, 2>;
 using Plan1024  = FftPlan<1024,  32, 32, 2>;

@@ -28,6 +28,31 @@
 namespace fosphor_b200 {
 
 namespace {
+#if defined(__x86_64__)
+/* non-temporal copy: the destination (page-locked staging memory the DMA engine reads next) is
+ * written around the caches, which saves the read-for-ownership of every destination line - one of
+ * the four trips a staged byte makes through host DRAM */
+__attribute__((target("avx2"))) void copy_stream_avx2(char *d, const char *s, size_t n)
+{
+	size_t head = (32 - (reinterpret_cast<uintptr_t>(d) & 31)) & 31;
+	if (head > n)
+		head = n;
+	memcpy(d, s, head);
+	d += head; s += head; n -= head;
+	for (; n >= 128; n -= 128, d += 128, s += 128) {
+		const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s));
+		const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + 32));
+		const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + 64));
+		const __m256i e = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + 96));
+		_mm256_stream_si256(reinterpret_cast<__m256i *>(d), a);
+		_mm256_stream_si256(reinterpret_cast<__m256i *>(d + 32), b);
+		_mm256_stream_si256(reinterpret_cast<__m256i *>(d + 64), c);
+		_mm256_stream_si256(reinterpret_cast<__m256i *>(d + 96), e);
+	}
+	_mm_sfence();
+	memcpy(d, s, n);
+}
+#endif
 constexpr size_t MIN_ITEM = 64 * 1024;
 /* how long an idle worker keeps polling before it sleeps: a streaming caller comes back every
  * 150-400 us (8 MiB per call at PCIe speed, a read-back in between); a sleeping worker costs
@@ -54,9 +79,18 @@ int copy_pool::default_threads()
 	int local_world = 1;
 	if (const char *v = getenv("LOCAL_WORLD_SIZE"))
 		local_world = atoi(v) > 0 ? atoi(v) : 1;
+	/* ... unless somebody already did: an affinity mask narrower than the machine is this process's
+	 * own share (bench.py binds each rank to its cores) */
+	const int online = (int)std::thread::hardware_concurrency();
+	if (online > 0 && cpus < online)
+		local_world = 1;
 	int t = cpus / local_world / 2;      /* the caller copies too; leave cores for the producer side */
 	if (t < 1) t = 1;
-	if (t > 8) t = 8;
+	/* measured on the GPU box (tools/e2e_probe.py, 8 MiB calls, 53 GB/s PCIe): 4 workers + the caller
+	 * keep up with the DMA engine (5 x 12 GB/s); 6, 8, 12 are each a little SLOWER (5.4 / 5.2 / 5.15 /
+	 * 4.98 Gsamples/s): the copy only has to keep pace, and more threads fight the DMA reads for
+	 * host memory bandwidth */
+	if (t > 4) t = 4;
 	return t;
 }
 
@@ -96,7 +130,12 @@ bool copy_pool::run_item()
 		const size_t off = (size_t)k * item_bytes_;
 		if (off < psz) {
 			const size_t n = psz - off < item_bytes_ ? psz - off : item_bytes_;
-			memcpy(dst_ + p0 + off, src_ + p0 + off, n);
+#if defined(__x86_64__)
+			if (nt_)
+				copy_stream_avx2(dst_ + p0 + off, src_ + p0 + off, n);
+			else
+#endif
+				memcpy(dst_ + p0 + off, src_ + p0 + off, n);
 		}
 		piece_done_[piece].fetch_add(1, std::memory_order_release);
 	}
@@ -130,8 +169,13 @@ void copy_pool::worker()
 	}
 }
 
-void copy_pool::start(void *dst, const void *src, size_t bytes, int pieces)
+void copy_pool::start(void *dst, const void *src, size_t bytes, int pieces, bool non_temporal)
 {
+#if defined(__x86_64__)
+	nt_ = non_temporal && __builtin_cpu_supports("avx2");
+#else
+	nt_ = false;
+#endif
 	if (pieces < 1) pieces = 1;
 	if (pieces > MAX_PIECES) pieces = MAX_PIECES;
 	dst_ = static_cast<char *>(dst);

@@ -40,8 +40,9 @@ public:
 
 	/* Start copying bytes from src to dst, cut into `pieces` equal parts (the last one takes the
 	 * remainder; 1 <= pieces <= MAX_PIECES) that complete in order.  Returns at once; the calling
-	 * thread helps from wait_piece().  One job at a time. */
-	void start(void *dst, const void *src, size_t bytes, int pieces);
+	 * thread helps from wait_piece().  One job at a time.  non_temporal: write the destination
+	 * around the caches (staging buffers the DMA engine reads next). */
+	void start(void *dst, const void *src, size_t bytes, int pieces, bool non_temporal = false);
 	/* Block until piece p (and all before it) has been copied. */
 	void wait_piece(int p);
 	/* start + wait for everything */
@@ -73,6 +74,7 @@ private:
 	const char *src_ = nullptr;
 	size_t bytes_ = 0, piece_bytes_ = 0, item_bytes_ = 0;
 	int pieces_ = 0, items_per_piece_ = 0, n_items_ = 0;
+	bool nt_ = false;                    /* non-temporal stores for this job */
 	std::atomic<int> next_item_{0};
 	std::atomic<int> piece_done_[MAX_PIECES];
 };

@@ -116,7 +116,7 @@ void fosphor_cu_power_range(int fft_len, int db_ref, int db_per_div, float *scal
  * returns (base_sink_c_impl.cc:170-174).  Page-locked sources are DMA'd in place;
  * pageable ones (the unmodified sink's FIFO, lib/fifo.cc:17-21) are staged by a
  * few copy threads, piece by piece, the DMA of a piece overlapping the copy of the
- * next (FOSPHOR_B200_COPY_THREADS, default min(8, cores/2)).  With
+ * next (FOSPHOR_B200_COPY_THREADS, default min(4, cores/2)).  With
  * FOSPHOR_B200_HOSTREG=1 the engine instead page-locks the caller's buffer where it
  * lies the first time it sees it - only for callers whose sample memory outlives the
  * engine, as the sink's FIFO does. */

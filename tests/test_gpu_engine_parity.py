@@ -319,6 +319,7 @@ def test_kernel_variants_are_bit_identical(torch_cuda, monkeypatch):
     variants = (("2", "0", "1", "256", "64", "1", "16", "1", "1"),     # fused kernel, one stream
                 ("0", "0", "1", "16", "16", "1", "16", "1", "2"),      # calls handed over in pairs
                 ("2", "0", "1", "256", "64", "1", "16", "1", "4"),     # ... in fours (short last group)
+                ("4", "0", "1", "64", "16", "1", "16", "1", "1"),      # grouped FFT kernel (8192 / 16384: warp-local late passes)
                 ("1", "1", "1", "64", "64", "1", "2", "1", "0"),       # two streams, slim co-resident accumulate CTAs
                 ("2", "1", "1", "256", "16", "1", "1", "1", "0"),
                 ("2", "1", "1", "256", "64", "1", "1", "0", "2"),      # two streams, full-size accumulate CTAs
