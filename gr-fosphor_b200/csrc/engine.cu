@@ -100,7 +100,7 @@ Tuning tuning_from_env()
 	if (t.acc_group != 1 && t.acc_group != 2 && t.acc_group != 4) t.acc_group = 0;
 	t.acc_mode = env_int("ACC", t.acc_mode);
 	t.acc_cols = env_int("ACC_COLS", 0);
-	if (t.acc_cols != 4 && t.acc_cols != 8 && t.acc_cols != 16 && t.acc_cols != 32) t.acc_cols = 0;
+	if (t.acc_cols != 4 && t.acc_cols != 8 && t.acc_cols != 16) t.acc_cols = 0;
 	{
 		const int b = env_int("ACC_BOX", t.acc_box_max);
 		t.acc_box_max = b >= 256 ? 256 : (b >= 64 ? 64 : (b >= 16 ? 16 : 0));
@@ -830,7 +830,6 @@ size_t fused_smem_need_cols(int cols, int n_bins, int batch, int gc)
 	switch (cols) {
 	case 4:  return fused_smem_need<4>(n_bins, batch, gc);
 	case 16: return fused_smem_need<16>(n_bins, batch, gc);
-	case 32: return fused_smem_need<32>(n_bins, batch, gc);
 	default: return fused_smem_need<8>(n_bins, batch, gc);
 	}
 }
@@ -887,20 +886,18 @@ int launch_accumulate_fused(fosphor_cu *e, const BatchTables *t, cudaStream_t st
 	const size_t smem_max = e->smem_optin;
 	while (gc > 1 && fused_smem_need_cols(e->acc_cols, a.n_bins, batch, gc) > smem_max)
 		gc >>= 1;
-	if (e->acc_cols > 8) {       /* wide tiles (few CTAs, the rest of the chip stays with the FFT kernel): one variant */
+	/* 16-column tiles (experiment knob ACC_COLS=16: N/16 CTAs leave more of the chip to the FFT kernel
+	 * beside them; cfg2 +1.7 %, within the run-to-run spread): one variant.  32-column tiles were 9x
+	 * SLOWER (32 CTAs: the per-SM L2 -> shared-memory path and a 2-box stage ring cannot feed them). */
+	if (e->acc_cols > 8)
 		gc = 1;
-		if (subr > 16 && e->acc_cols == 32)
-			subr = 16;
-	}
 	/* warp roles (counters / cell updaters): 16 / 8, or 8 / 16 when a call has more cells to update
 	 * than rows to count (ncu of cfg3, B = 256, K = 512: the counter warps spent half their time
 	 * waiting for the updaters to hand the hit tiles back) */
 	int roles = e->tn.acc_roles;
 	if (roles == 0)
 		roles = (gc == 4 && a.n_bins >= batch) ? 2 : 1;
-	if (e->acc_cols == 32)
-		err = fused_dispatch<32, 16, ACC_UW, 1>(e, a, st, boxr, subr);
-	else if (e->acc_cols == 16)
+	if (e->acc_cols == 16)
 		err = fused_dispatch<16, 16, ACC_UW, 1>(e, a, st, boxr, subr);
 	else if (e->acc_cols == 4)
 		err = slim ? fused_dispatch<4, ACC_FW_SLIM, ACC_UW_SLIM>(e, a, st, boxr, subr)

@@ -274,8 +274,9 @@ struct StreamCfg {
 	static constexpr int BUF_ELEMS = P::SM_ELEMS * SPW;           /* >= SPW * N: holds inputs, then the exchange */
 	static constexpr size_t BUF_BYTES_ALL = sizeof(float2) * (size_t)BUF_ELEMS * 2 * WARPS;
 	static constexpr size_t SMEM = BUF_BYTES_ALL + 8 * 2 * WARPS;
-	/* TWREG variant: + the window, shared by the CTA */
-	static constexpr size_t SMEM_TWREG = SMEM + sizeof(float) * P::N;
+	/* TWREG variant: + the window, shared by the CTA, every tap twice (w, w): one 64-bit load feeds
+	 * one packed multiply (FMUL2) of the complex sample */
+	static constexpr size_t SMEM_TWREG = SMEM + sizeof(float2) * P::N;
 	static constexpr unsigned IN_BYTES = sizeof(float2) * P::N;   /* one spectrum */
 };
 
@@ -313,12 +314,14 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 	constexpr int SPW = C::SPW;
 	const int q1 = lane / P::NB1, i1 = lane % P::NB1;    /* pass 1: spectrum slot and butterfly of this lane */
 	float wreg[TWREG ? 1 : R0];
-	const float *swin = reinterpret_cast<const float *>(smem_raw + C::SMEM);
+	const float2 *swin = reinterpret_cast<const float2 *>(smem_raw + C::SMEM);
 	float2 twreg[TWREG ? R1 : 1];
 	if constexpr (TWREG) {
-		float *sw = reinterpret_cast<float *>(smem_raw + C::SMEM);
-		for (int i = threadIdx.x; i < N; i += C::THREADS)
-			sw[i] = __ldg(&win[i]);
+		float2 *sw = reinterpret_cast<float2 *>(smem_raw + C::SMEM);
+		for (int i = threadIdx.x; i < N; i += C::THREADS) {
+			const float w = __ldg(&win[i]);
+			sw[i] = make_float2(w, w);
+		}
 		__syncthreads();
 		if (q1 < SPW) {
 #pragma unroll
@@ -374,8 +377,10 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 #pragma unroll
 				for (int t = 0; t < R0; t++) {
 					const float2 x = bq[lane + t * P::NB0];
-					const float w = TWREG ? swin[lane + t * P::NB0] : wreg[t];
-					v0[t] = win_mul(x, w);               /* fft.cl:416-417 */
+					if constexpr (TWREG)
+						v0[t] = __fmul2_rn(x, swin[lane + t * P::NB0]);   /* fft.cl:416-417, both components at once */
+					else
+						v0[t] = win_mul(x, wreg[t]);
 				}
 			}
 			__syncwarp();                   /* inputs consumed: the slot becomes the exchange buffer */

@@ -86,6 +86,22 @@ __device__ __forceinline__ float2 mul_w64(float2 v)
 	}
 }
 
+/* Complex add / subtract as ONE packed instruction each (Blackwell FADD2 / FFMA2, add.rn.f32x2 and
+ * fma.rn.f32x2 on a 64-bit register pair): the butterflies' 4 scalar FADDs become 2 issue slots.  The
+ * kernels are issue bound as soon as the SM clock sags under the board's power cap (sustained runs:
+ * ~1.55 GHz), so halving 960 of the N = 1024 kernel's ~2000 instructions is worth more than it looks
+ * at burst clocks, where HBM is the roof.  Roundings are those of the scalar form: a + b and
+ * fma(b, -1, a) = round(a - b), each component on its own. */
+__device__ __forceinline__ float2 cadd(float2 a, float2 b)
+{
+	return __fadd2_rn(a, b);
+}
+
+__device__ __forceinline__ float2 csub(float2 a, float2 b)
+{
+	return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a);
+}
+
 /* One DIF level of size M on registers v[BASE .. BASE+M), then recurse. */
 template <int M, int BASE, int R>
 __device__ __forceinline__ void dif_level(float2 (&v)[R])
@@ -95,8 +111,8 @@ __device__ __forceinline__ void dif_level(float2 (&v)[R])
 		static_for<0, H>([&](auto jc) {
 			constexpr int j = decltype(jc)::value;
 			const float2 a = v[BASE + j], b = v[BASE + j + H];
-			v[BASE + j] = make_float2(a.x + b.x, a.y + b.y);
-			v[BASE + j + H] = mul_w64<j * (64 / M)>(make_float2(a.x - b.x, a.y - b.y));
+			v[BASE + j] = cadd(a, b);
+			v[BASE + j + H] = mul_w64<j * (64 / M)>(csub(a, b));
 		});
 		dif_level<H, BASE, R>(v);
 		dif_level<H, BASE + H, R>(v);
