@@ -613,11 +613,13 @@ def run_e2e(torch, dist, dev, local, world, args, lib_path, FosphorCL, Fosphor, 
         return world * reps * frame_samples / el / 1e6, el / reps * 1e3
 
     frames = args.e2e_frames
-    v_page, ms_frame = dropin_frames(frame.ctypes.data, frames)
+    v_page, ms_frame = dropin_frames(frame.ctypes.data, frames)                       # library defaults
+    v_staged, _ = dropin_frames(frame.ctypes.data, frames // 2, env={"FOSPHOR_B200_HOSTREG": "0"})
     v_reg, _ = dropin_frames(frame.ctypes.data, frames // 2, env={"FOSPHOR_B200_HOSTREG": "1"})
     pinned = torch.from_numpy(frame.view(np.float32)).pin_memory()
     v_pin, _ = dropin_frames(pinned.data_ptr(), frames // 2)
-    one_thread, _ = dropin_frames(frame.ctypes.data, max(8, frames // 8), env={"FOSPHOR_B200_COPY_THREADS": "1"})
+    one_thread, _ = dropin_frames(frame.ctypes.data, max(8, frames // 8),
+                                  env={"FOSPHOR_B200_COPY_THREADS": "1", "FOSPHOR_B200_HOSTREG": "0"})
 
     # the parameterised engine from page-locked memory: 48 calls of K=256 + finish, and the raw stream
     k, calls = N_BINS, 48
@@ -640,20 +642,26 @@ def run_e2e(torch, dist, dev, local, world, args, lib_path, FosphorCL, Fosphor, 
             "h2d_bytes_per_step": 8 * frame_samples, "d2h_bytes_per_step": 4 * (WF_ROWS * n + REF_BINS * n + 4 * n),
             "step": "one sink frame: 8 x fosphor_cl_process(1024 spectra) + fosphor_cl_finish; %d frames timed" % frames,
             "ms_per_frame": ms_frame,
-            "api": "the drop-in's fosphor_cl_* symbols (lib/fosphor/cl.h:22-32), PAGEABLE numpy input staged by the "
-                   "engine's copy threads, 128 bins, 1024 rows - the same calls, geometry and memory type as "
-                   "--impl reference",
+            "api": "the drop-in's fosphor_cl_* symbols (lib/fosphor/cl.h:22-32), PAGEABLE numpy input, library defaults, "
+                   "128 bins, 1024 rows - the same calls, geometry and memory type as --impl reference.  Defaults: a "
+                   "call range is staged by the copy threads on first sight and page-locked where it lies on second "
+                   "sight, every later use checked against the physical page numbers recorded then (needs "
+                   "/proc/self/pagemap with PFNs, i.e. a privileged process such as this one: root=%s; otherwise "
+                   "always staged)" % (os.geteuid() == 0),
             "pcie_GBps": v_page * 8e6 / 1e9 / world,
             "variants": {
                 "dropin_pageable_default": v_page,
-                "dropin_pageable_one_copy_thread": one_thread,
-                "dropin_pageable_hostreg": v_reg,
+                "dropin_pageable_always_staged": v_staged,
+                "dropin_pageable_always_staged_one_copy_thread": one_thread,
+                "dropin_pageable_hostreg_forced": v_reg,
                 "dropin_page_locked_input": v_pin,
                 "engine_raw_stream_in_engine_overlap": v_raw,
-                "notes": "hostreg: FOSPHOR_B200_HOSTREG=1 page-locks the caller's buffer on first sight (opt-in, "
-                         "for long-lived sample rings like the sink's FIFO); page_locked: cudaHostAlloc'ed source "
-                         "(the pinned FIFO of SURVEY 8f#2); raw stream: fosphor_cu_process_host_raw, hop=N/4, each "
-                         "raw sample crosses PCIe once (x4 fewer bytes per FFT sample)"}}
+                "notes": "always_staged: FOSPHOR_B200_HOSTREG=0 (what an unprivileged process gets by default: copy "
+                         "threads, three trips through host DRAM per byte - host-memory bound when several GPUs share "
+                         "a host); hostreg_forced: FOSPHOR_B200_HOSTREG=1 (first sight, no page-number check: for "
+                         "callers that vouch for their buffers, like the sink with its long-lived FIFO); page_locked: "
+                         "cudaHostAlloc'ed source (the pinned FIFO of SURVEY 8f#2); raw stream: "
+                         "fosphor_cu_process_host_raw, hop=N/4, each raw sample crosses PCIe once"}}
 
 
 def run_reference(args):

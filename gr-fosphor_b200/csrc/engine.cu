@@ -20,6 +20,9 @@
 #include <unordered_map>
 #include <vector>
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -69,7 +72,11 @@ struct Tuning {
 	int fft_r64 = 0;           /* FFT_R64: two-pass radix-64 plans for N = 2048 / 4096 */
 	int fft_pf = -1;           /* FFT_PF: L2 prefetch distance of the plain FFT kernel (-1 = resident CTAs) */
 	int fft_ctas_per_sm = 0;   /* FFT_CTAS: CTAs/SM of the persistent FFT kernel (0 = automatic) */
-	int hostreg = 0;           /* HOSTREG: page-lock pageable caller buffers on first sight (see upload_staged) */
+	int hostreg = -1;          /* HOSTREG: page-lock pageable caller buffers where they lie (see hostreg_cover):
+	                            * 1 on first sight, trusting the caller to keep them alive; 0 never (always stage);
+	                            * -1 automatic: on SECOND sight, and only where the physical page numbers can be read
+	                            * (/proc/self/pagemap, i.e. a privileged process) so that every use can be checked
+	                            * against a buffer that was freed and reallocated meanwhile */
 	int copy_threads = 0;      /* COPY_THREADS: staging-copy threads (0 = automatic) */
 	int copy_nt = 0;           /* COPY_NT: non-temporal stores into the staging slots.  Off: with plain stores the
 	                            * slots (4 x 8 MiB) stay in the host's last-level cache and the DMA engine reads them
@@ -122,8 +129,9 @@ Tuning tuning_from_env()
 	return t;
 }
 
-struct HostRange {             /* caller memory page-locked by the engine (opt-in) */
+struct HostRange {             /* caller memory page-locked by the engine */
 	uintptr_t lo, hi;
+	std::vector<uint64_t> pfn; /* physical page numbers at registration (automatic mode), one per 4 KiB page */
 };
 
 struct BatchTables {
@@ -216,6 +224,9 @@ struct fosphor_cu {
 	std::unique_ptr<copy_pool> pool;     /* staging-copy threads, started on the first pageable call */
 	std::vector<HostRange> hostreg;      /* caller memory page-locked on the fly (tn.hostreg) */
 	size_t hostreg_bytes = 0;
+	std::vector<HostRange> seen;         /* automatic mode: pageable call ranges staged recently (second sight promotes) */
+	int pagemap_fd = -2;                 /* /proc/self/pagemap: -2 not tried, -1 unusable (no PFNs for this process) */
+	int hostreg_stale = 0;               /* registrations found stale: after a few the engine stops registering */
 	unsigned long long staged_calls = 0, direct_calls = 0;   /* diagnostics: how the host samples travelled */
 	/* results on their way to pageable caller memory (finish): D2H into page-locked memory, then the copy pool */
 	float *h_out = nullptr;
@@ -1177,43 +1188,129 @@ copy_pool *get_pool(fosphor_cu *e)
 	return e->pool.get();
 }
 
-/* Opt-in (FOSPHOR_B200_HOSTREG=1): page-lock the caller's buffer where it lies, once, and DMA
- * straight out of it from then on.  Right for callers whose sample memory lives as long as the
- * engine - the reference sink's FIFO does (one 16 MiB ring allocated in the constructor,
- * lib/base_sink_c_impl.cc:58, freed after the worker thread that owns the engine has been joined) -
- * and WRONG for buffers that are freed while registered: the driver keeps the old pages pinned and
- * a later allocation at the same address would be read stale.  Hence not the default.  Ranges are
- * registered page-wise, never overlapping; true iff [p, p + bytes) is now inside ONE registered
- * range. */
+/* ---- page-locking the caller's buffer where it lies --------------------------------------------
+ * cudaHostRegister once, DMA straight out of the caller's memory from then on: no CPU copy, one trip
+ * through host DRAM instead of three (8 GPUs on one host: 21 vs 5.6 Gsamples/s, the staged path is
+ * host-memory bound there).  Right for callers whose sample memory lives as long as the engine - the
+ * reference sink's FIFO does (one 16 MiB ring allocated in the constructor, lib/base_sink_c_impl.cc:58,
+ * freed after the worker thread that owns the engine has been joined) - and DANGEROUS for buffers
+ * that are freed while registered: the driver keeps the old pages pinned, and a later allocation at
+ * the same address would be read stale.  Therefore:
+ *   HOSTREG=1   the caller vouches for its buffers: register on first sight;
+ *   automatic   register a call range on SECOND sight, record the physical page numbers of the range
+ *               (/proc/self/pagemap - readable with PFNs only for a privileged process; otherwise the
+ *               automatic mode never registers) and compare a few of them before EVERY use: a freed and
+ *               reallocated buffer has other pages, is unregistered and staged (three strikes and
+ *               the engine stops registering);
+ *   HOSTREG=0   never.
+ * Ranges are registered page-wise, never overlapping, merged when they touch. */
+uint64_t page_frame(fosphor_cu *e, uintptr_t addr)
+{
+	if (e->pagemap_fd == -2) {
+		e->pagemap_fd = open("/proc/self/pagemap", O_RDONLY | O_CLOEXEC);
+		if (e->pagemap_fd >= 0) {
+			int probe = 1;                    /* a page of our own stack: present by construction */
+			uint64_t ent = 0;
+			const uintptr_t a = reinterpret_cast<uintptr_t>(&probe);
+			if (pread(e->pagemap_fd, &ent, 8, (off_t)(a / 4096 * 8)) != 8 || !(ent >> 63) ||
+			    (ent & ((1ull << 55) - 1)) == 0) {
+				close(e->pagemap_fd);             /* PFNs are hidden from this process */
+				e->pagemap_fd = -1;
+			}
+		} else {
+			e->pagemap_fd = -1;
+		}
+	}
+	if (e->pagemap_fd < 0)
+		return 0;
+	uint64_t ent = 0;
+	if (pread(e->pagemap_fd, &ent, 8, (off_t)(addr / 4096 * 8)) != 8 || !(ent >> 63))
+		return 0;
+	return ent & ((1ull << 55) - 1);
+}
+
+void hostreg_drop(fosphor_cu *e, size_t idx)
+{
+	HostRange &r = e->hostreg[idx];
+	if (cudaHostUnregister(reinterpret_cast<void *>(r.lo)) != cudaSuccess)
+		cudaGetLastError();
+	e->hostreg_bytes -= r.hi - r.lo;
+	e->hostreg.erase(e->hostreg.begin() + (long)idx);
+}
+
+/* true iff [p, p + bytes) is inside ONE range registered by this engine - and, in automatic mode,
+ * still backed by the pages that were registered */
 bool hostreg_cover(fosphor_cu *e, const void *p, size_t bytes)
 {
 	const uintptr_t page = 4096;
 	uintptr_t lo = reinterpret_cast<uintptr_t>(p) & ~(page - 1);
 	uintptr_t hi = (reinterpret_cast<uintptr_t>(p) + bytes + page - 1) & ~(page - 1);
-	for (const HostRange &r : e->hostreg)
-		if (lo >= r.lo && hi <= r.hi)
-			return true;
+	const bool automatic = e->tn.hostreg < 0;
+	if (automatic && (e->hostreg_stale >= 3 || (e->pagemap_fd == -1)))
+		return false;
+	for (size_t i = 0; i < e->hostreg.size(); i++) {
+		HostRange &r = e->hostreg[i];
+		if (lo < r.lo || hi > r.hi)
+			continue;
+		if (!r.pfn.empty()) {
+			/* first, last and two inner pages of THIS call's range: a buffer that was freed and
+			 * reallocated has none of its old pages (they are still pinned by the registration) */
+			const uintptr_t n = (hi - lo) / page;
+			const uintptr_t probe[4] = {lo, lo + (n / 3) * page, lo + (2 * n / 3) * page, hi - page};
+			for (uintptr_t a : probe)
+				if (page_frame(e, a) != r.pfn[(a - r.lo) / page]) {
+					hostreg_drop(e, i);
+					e->hostreg_stale++;
+					return false;                 /* staged this time; it may be registered afresh later */
+				}
+		}
+		return true;
+	}
+	if (automatic) {
+		/* second sight promotes: one-shot buffers are never registered (1.3 ms per 8 MiB) */
+		if (page_frame(e, lo) == 0)
+			return false;
+		bool known = false;
+		for (const HostRange &r : e->seen)
+			if (r.lo == lo && r.hi == hi)
+				known = true;
+		if (!known) {
+			if (e->seen.size() >= 16)
+				e->seen.erase(e->seen.begin());
+			e->seen.push_back({lo, hi, {}});
+			return false;
+		}
+	}
 	/* grow to the hull of everything it touches: the sink's ring is one allocation, its chunks abut */
-	std::vector<HostRange> keep;
-	for (const HostRange &r : e->hostreg) {
+	for (size_t i = 0; i < e->hostreg.size();) {
+		const HostRange &r = e->hostreg[i];
 		if (r.hi < lo || r.lo > hi) {
-			keep.push_back(r);
+			i++;
 			continue;
 		}
-		if (cudaHostUnregister(reinterpret_cast<void *>(r.lo)) != cudaSuccess)
-			cudaGetLastError();
-		e->hostreg_bytes -= r.hi - r.lo;
 		lo = r.lo < lo ? r.lo : lo;
 		hi = r.hi > hi ? r.hi : hi;
+		hostreg_drop(e, i);
 	}
-	e->hostreg.swap(keep);
 	if (e->hostreg_bytes + (hi - lo) > HOSTREG_BUDGET)
 		return false;
 	if (cudaHostRegister(reinterpret_cast<void *>(lo), hi - lo, cudaHostRegisterDefault) != cudaSuccess) {
 		cudaGetLastError();
 		return false;
 	}
-	e->hostreg.push_back({lo, hi});
+	HostRange nr{lo, hi, {}};
+	if (automatic) {
+		nr.pfn.resize((hi - lo) / page);
+		std::vector<uint64_t> ent(nr.pfn.size());
+		const ssize_t want = (ssize_t)(8 * ent.size());
+		if (pread(e->pagemap_fd, ent.data(), (size_t)want, (off_t)(lo / page * 8)) != want) {
+			cudaHostUnregister(reinterpret_cast<void *>(lo));
+			return false;
+		}
+		for (size_t i = 0; i < ent.size(); i++)
+			nr.pfn[i] = (ent[i] >> 63) ? (ent[i] & ((1ull << 55) - 1)) : 0;
+	}
+	e->hostreg.push_back(std::move(nr));
 	e->hostreg_bytes += hi - lo;
 	return true;
 }
@@ -1237,8 +1334,21 @@ int upload_staged(fosphor_cu *e, const float2 *src, size_t n_samples, float2 **d
 	const size_t bytes = sizeof(float2) * n_samples;
 	/* previous reader of d_in[s] done (which implies the H2D that filled it, hence h_in[s] too) */
 	CU_CHECK(e, cudaEventSynchronize(e->slot_free[s]));
-	bool direct = is_pinned_range(src, bytes) ||
-	              (e->tn.hostreg > 0 && hostreg_cover(e, src, bytes) && is_pinned_range(src, bytes));
+	bool own = false;                        /* inside a range this engine registered: must be re-validated */
+	{
+		const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+		for (const HostRange &r : e->hostreg)
+			if (a < r.hi && a + bytes > r.lo)
+				own = true;
+	}
+	bool direct;
+	if (own)
+		direct = hostreg_cover(e, src, bytes) && is_pinned_range(src, bytes);
+	else if (is_pinned_range(src, bytes))
+		direct = true;                       /* page-locked by the caller (pinned FIFO, cudaHostRegister) */
+	else
+		direct = e->tn.hostreg != 0 && bytes >= ((size_t)1 << 20) && hostreg_cover(e, src, bytes) &&
+		         is_pinned_range(src, bytes);
 	if (direct && cudaMemcpyAsync(e->d_in[s], src, bytes, cudaMemcpyHostToDevice, e->copy_stream) != cudaSuccess) {
 		cudaGetLastError();               /* e.g. a range stitched from two registrations: stage it instead */
 		direct = false;
@@ -1248,7 +1358,15 @@ int upload_staged(fosphor_cu *e, const float2 *src, size_t n_samples, float2 **d
 		e->await_slot = s;
 		e->direct_calls++;
 	} else {
-		const size_t piece = (size_t)e->tn.stage_piece_kb << 10;
+		/* with nothing in flight on the copy stream (the first call after a finish) the DMA engine waits
+		 * for the first piece: make that one small; behind a running DMA larger pieces cost fewer requests */
+		size_t piece = (size_t)e->tn.stage_piece_kb << 10;
+		if (piece > ((size_t)1 << 20)) {
+			if (cudaStreamQuery(e->copy_stream) == cudaSuccess)
+				piece = (size_t)1 << 20;
+			else
+				cudaGetLastError();       /* cudaErrorNotReady is an answer, not an error to find later */
+		}
 		copy_pool *pool = bytes >= ((size_t)1 << 20) ? get_pool(e) : nullptr;
 		if (pool) {
 			int pieces = (int)((bytes + piece - 1) / piece);
@@ -1401,6 +1519,8 @@ void fosphor_cu_destroy(struct fosphor_cu *e)
 	for (const HostRange &r : e->hostreg)
 		if (cudaHostUnregister(reinterpret_cast<void *>(r.lo)) != cudaSuccess)
 			cudaGetLastError();
+	if (e->pagemap_fd >= 0)
+		close(e->pagemap_fd);
 	if (e->d_ring != e->d_wf)
 		cudaFree(e->d_ring);
 	cudaFree(e->d_twg);

@@ -113,13 +113,19 @@ void fosphor_cu_power_range(int fft_len, int db_ref, int db_per_div, float *scal
 
 /* One reference-style call on HOST samples: len complex samples = n_spectra
  * pre-overlapped windows (cl.c:870-968).  The source buffer is free when the call
- * returns (base_sink_c_impl.cc:170-174).  Page-locked sources are DMA'd in place;
- * pageable ones (the unmodified sink's FIFO, lib/fifo.cc:17-21) are staged by a
- * few copy threads, piece by piece, the DMA of a piece overlapping the copy of the
- * next (FOSPHOR_B200_COPY_THREADS, default min(4, cores/2)).  With
- * FOSPHOR_B200_HOSTREG=1 the engine instead page-locks the caller's buffer where it
- * lies the first time it sees it - only for callers whose sample memory outlives the
- * engine, as the sink's FIFO does. */
+ * returns (base_sink_c_impl.cc:170-174).  How the samples travel:
+ *   - page-locked source (cudaHostAlloc / cudaHostRegister / fosphor_fifo_*): DMA in place;
+ *   - pageable source (the unmodified sink's FIFO, lib/fifo.cc:17-21): staged by a few copy
+ *     threads, piece by piece, the DMA of a piece overlapping the copy of the next
+ *     (FOSPHOR_B200_COPY_THREADS, default min(4, cores/2)) - or, better, page-locked by the
+ *     engine where it lies and DMA'd in place from then on.  FOSPHOR_B200_HOSTREG selects:
+ *       unset  automatic: a call range is registered the second time it is seen, and only if the
+ *              process can read its physical page numbers (/proc/self/pagemap: privileged
+ *              processes); every later use compares a few of them, so a buffer that was freed and
+ *              reallocated at the same address is detected, unregistered and staged instead;
+ *       1      register on first sight without that check - for callers whose sample memory
+ *              outlives the engine, as the sink's FIFO does (the setting for an unprivileged sink);
+ *       0      always stage. */
 int fosphor_cu_process_host(struct fosphor_cu *e, const void *samples_host, int len);
 
 /* One call on DEVICE-resident samples.  Spectrum s is read at

@@ -110,20 +110,22 @@ def test_finish_new_rows_refreshes_only_what_changed(torch_cuda):
 
 
 def test_pageable_host_feed_matches_page_locked(torch_cuda, monkeypatch):
-    """The unmodified sink hands pageable memory (lib/fifo.cc:17-21): staged by the copy threads in
-    pieces.  Same bits as a page-locked source (DMA in place) and as FOSPHOR_B200_HOSTREG=1 (the
-    engine page-locks the caller's ring on first sight); the source may be scribbled on as soon as
-    the call returns."""
+    """The unmodified sink hands pageable memory (lib/fifo.cc:17-21).  FOSPHOR_B200_HOSTREG=0: staged by
+    the copy threads in pieces; =1: the engine page-locks the caller's ring on first sight and DMAs in
+    place; default (automatic): staged on first sight, registered on second sight where the process can
+    read its physical page numbers (else always staged).  Same bits as a page-locked source in every
+    mode; the source may be scribbled on as soon as the call returns."""
     torch = torch_cuda
-    n, sizes = 1024, (1024, 1024, 256, 1024, 16, 1024)
+    n, sizes = 1024, (1024, 1024, 256, 1024, 16, 1024, 1024, 1024)
     x = signals.noise_tones(n * sum(sizes), seed=31)
     pinned = torch.from_numpy(x.view(np.float32).copy()).pin_memory()
-    outs, stats = [], []
-    for mode in ("pageable", "pinned", "hostreg"):
-        if mode == "hostreg":
+    outs, stats = [], {}
+    for mode in ("staged", "pinned", "hostreg", "auto"):
+        monkeypatch.delenv("FOSPHOR_B200_HOSTREG", raising=False)
+        if mode == "staged":
+            monkeypatch.setenv("FOSPHOR_B200_HOSTREG", "0")
+        elif mode == "hostreg":
             monkeypatch.setenv("FOSPHOR_B200_HOSTREG", "1")
-        else:
-            monkeypatch.delenv("FOSPHOR_B200_HOSTREG", raising=False)
         e = _engine()
         ring = np.empty(2 * 1024 * n, np.complex64)            # a long-lived pageable "FIFO"
         pos = 0
@@ -138,16 +140,61 @@ def test_pageable_host_feed_matches_page_locked(torch_cuda, monkeypatch):
             pos += s * n
         _, h = e.finish()
         outs.append({k: v.copy() for k, v in h.items()})
-        stats.append(e.host_feed_stats())
+        stats[mode] = e.host_feed_stats()
         e.close()
         del ring
     for o in outs[1:]:
         for key in ("waterfall", "histogram", "spectrum"):
             assert np.array_equal(outs[0][key], o[key]), key
-    assert stats[0]["staged_calls"] == len(sizes) and stats[0]["direct_calls"] == 0
-    assert stats[0]["copy_threads"] >= 1                       # 8 MiB calls went through the pool
-    assert stats[1]["direct_calls"] == len(sizes) and stats[1]["staged_calls"] == 0
-    assert stats[2]["direct_calls"] == len(sizes) and stats[2]["staged_calls"] == 0
+    calls = len(sizes)
+    assert stats["staged"]["staged_calls"] == calls and stats["staged"]["direct_calls"] == 0
+    assert stats["staged"]["copy_threads"] >= 1                # 8 MiB calls went through the pool
+    assert stats["pinned"]["direct_calls"] == calls and stats["pinned"]["staged_calls"] == 0
+    # forced: the two halves of the ring are registered on first sight (merged into one hull), every
+    # later call - also the small ones - lies inside
+    assert stats["hostreg"]["direct_calls"] == calls and stats["hostreg"]["staged_calls"] == 0
+    assert stats["auto"]["direct_calls"] + stats["auto"]["staged_calls"] == calls
+    if os.geteuid() == 0:                                      # PFNs readable: second sight was registered
+        assert stats["auto"]["direct_calls"] >= 3, stats["auto"]
+
+
+def test_automatic_host_registration_survives_freed_and_reallocated_buffers(torch_cuda, monkeypatch):
+    """The hazard of page-locking caller memory: the caller unmaps a registered buffer, a new mapping
+    lands at the same address, the stale registration would DMA the old (still pinned) pages.  The
+    automatic mode compares physical page numbers before every use: results must equal the staged
+    path's however often the buffer is replaced.  Buffers are real mmap()s, unmapped after each
+    generation (an 8 MiB malloc may be served from the heap and keep its pages)."""
+    import mmap
+    n, b = 1024, 1024
+    size = 8 * b * n
+    monkeypatch.delenv("FOSPHOR_B200_HOSTREG", raising=False)
+    auto = _engine()
+    monkeypatch.setenv("FOSPHOR_B200_HOSTREG", "0")
+    staged = _engine()
+    addrs, reused = [], 0
+    for gen in range(6):
+        mm = mmap.mmap(-1, size, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+        buf = np.frombuffer(mm, dtype=np.complex64)
+        ptr = buf.ctypes.data
+        reused += ptr in addrs
+        addrs.append(ptr)
+        for rep in range(3):                                   # seen, registered (if PFNs are readable), used
+            buf[:] = signals.noise_tones(b * n, seed=100 + 10 * gen + rep)
+            for e in (auto, staged):
+                assert e.process_host_ptr(ptr, b * n) == 0
+        ha = {k: v.copy() for k, v in auto.finish()[1].items()}
+        hs = staged.finish()[1]
+        for key in ("waterfall", "histogram", "spectrum"):
+            assert np.array_equal(ha[key], hs[key]), (gen, key)
+        del buf
+        mm.close()                                             # munmap: the registration (if any) is now stale
+    st = auto.host_feed_stats()
+    print("mappings that landed on an earlier address: %d of 5; automatic mode: %s" % (reused, st))
+    if os.geteuid() == 0 and reused:
+        # stale registrations were found and dropped: those calls were staged, not DMA'd from dead pages
+        assert st["staged_calls"] >= 1 + reused, st
+    auto.close()
+    staged.close()
 
 
 def test_export_maxhold_on_side_stream(torch_cuda):
