@@ -1315,6 +1315,23 @@ bool hostreg_cover(fosphor_cu *e, const void *p, size_t bytes)
 	return true;
 }
 
+/* May the DMA engine work on [p, p + bytes) of the caller's memory in place?  Page-locked by the
+ * caller: yes.  Inside a range this engine registered: after re-validation.  Otherwise, if the
+ * policy allows and the range is worth it, register it now. */
+bool host_range_direct(fosphor_cu *e, const void *p, size_t bytes, size_t min_bytes)
+{
+	bool own = false;
+	const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+	for (const HostRange &r : e->hostreg)
+		if (a < r.hi && a + bytes > r.lo)
+			own = true;
+	if (own)
+		return hostreg_cover(e, p, bytes) && is_pinned_range(p, bytes);
+	if (is_pinned_range(p, bytes))
+		return true;                         /* page-locked by the caller (pinned FIFO, cudaHostRegister) */
+	return e->tn.hostreg != 0 && bytes >= min_bytes && hostreg_cover(e, p, bytes) && is_pinned_range(p, bytes);
+}
+
 /* Host samples -> device slot.  The source buffer is free when the process call returns (reference
  * contract, base_sink_c_impl.cc:170-174).
  *   page-locked source (cudaHostAlloc / cudaHostRegister, e.g. the pinned FIFO, or a range the
@@ -1334,21 +1351,7 @@ int upload_staged(fosphor_cu *e, const float2 *src, size_t n_samples, float2 **d
 	const size_t bytes = sizeof(float2) * n_samples;
 	/* previous reader of d_in[s] done (which implies the H2D that filled it, hence h_in[s] too) */
 	CU_CHECK(e, cudaEventSynchronize(e->slot_free[s]));
-	bool own = false;                        /* inside a range this engine registered: must be re-validated */
-	{
-		const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-		for (const HostRange &r : e->hostreg)
-			if (a < r.hi && a + bytes > r.lo)
-				own = true;
-	}
-	bool direct;
-	if (own)
-		direct = hostreg_cover(e, src, bytes) && is_pinned_range(src, bytes);
-	else if (is_pinned_range(src, bytes))
-		direct = true;                       /* page-locked by the caller (pinned FIFO, cudaHostRegister) */
-	else
-		direct = e->tn.hostreg != 0 && bytes >= ((size_t)1 << 20) && hostreg_cover(e, src, bytes) &&
-		         is_pinned_range(src, bytes);
+	bool direct = host_range_direct(e, src, bytes, (size_t)1 << 20);
 	if (direct && cudaMemcpyAsync(e->d_in[s], src, bytes, cudaMemcpyHostToDevice, e->copy_stream) != cudaSuccess) {
 		cudaGetLastError();               /* e.g. a range stitched from two registrations: stage it instead */
 		direct = false;
@@ -1425,32 +1428,35 @@ struct OutSeg {
 
 int download(fosphor_cu *e, const OutSeg *segs, int n)
 {
-	size_t total = 0;
-	bool all_pinned = true;
-	for (int i = 0; i < n; i++) {
-		total += segs[i].bytes;
-		if (segs[i].bytes && !is_pinned_range(segs[i].host, segs[i].bytes))
-			all_pinned = false;
+	/* the caller's result images are long-lived (self->img_*, fosphor.c:52-54): page-locked where they
+	 * lie under the same policy as the sample buffers, the D2H then lands in them directly; what is
+	 * left (small or unregistered segments) goes through the bounce buffer */
+	bool direct[8] = {};
+	size_t bounce = 0;
+	for (int i = 0; i < n && i < 8; i++) {
+		direct[i] = segs[i].bytes == 0 || host_range_direct(e, segs[i].host, segs[i].bytes, (size_t)256 << 10);
+		if (!direct[i])
+			bounce += segs[i].bytes;
 	}
-	copy_pool *pool = (all_pinned || total < ((size_t)256 << 10)) ? nullptr : get_pool(e);
-	if (!pool) {
-		for (int i = 0; i < n; i++)
-			if (segs[i].bytes)
-				CU_CHECK(e, cudaMemcpyAsync(segs[i].host, segs[i].dev, segs[i].bytes, cudaMemcpyDeviceToHost, e->stream));
+	for (int i = 0; i < n; i++)
+		if (direct[i] && segs[i].bytes)
+			CU_CHECK(e, cudaMemcpyAsync(segs[i].host, segs[i].dev, segs[i].bytes, cudaMemcpyDeviceToHost, e->stream));
+	if (bounce == 0) {
 		CU_CHECK(e, cudaStreamSynchronize(e->stream));   /* cl.c:1052 */
 		return 0;
 	}
-	if (e->h_out_bytes < total) {
+	copy_pool *pool = bounce < ((size_t)256 << 10) ? nullptr : get_pool(e);
+	if (e->h_out_bytes < bounce) {
 		if (e->h_out)
 			cudaFreeHost(e->h_out);
 		e->h_out = nullptr;
 		e->h_out_bytes = 0;
-		CU_CHECK(e, cudaMallocHost(&e->h_out, total));
-		e->h_out_bytes = total;
+		CU_CHECK(e, cudaMallocHost(&e->h_out, bounce));
+		e->h_out_bytes = bounce;
 	}
 	/* cut into at most OUT_CHUNKS chunks of >= 1 MiB; the D2H of chunk c+1 runs while the copy
 	 * threads move chunk c out of the bounce buffer */
-	size_t chunk = (total + OUT_CHUNKS - 1) / OUT_CHUNKS;
+	size_t chunk = (bounce + OUT_CHUNKS - 1) / OUT_CHUNKS;
 	if (chunk < ((size_t)1 << 20))
 		chunk = (size_t)1 << 20;
 	struct Piece { void *host; size_t off, bytes; };
@@ -1458,7 +1464,9 @@ int download(fosphor_cu *e, const OutSeg *segs, int n)
 	int np = 0;
 	char *hp = reinterpret_cast<char *>(e->h_out);
 	size_t off = 0;
-	for (int i = 0; i < n; i++)
+	for (int i = 0; i < n; i++) {
+		if (direct[i])
+			continue;
 		for (size_t o = 0; o < segs[i].bytes; o += chunk) {
 			const size_t nb = segs[i].bytes - o < chunk ? segs[i].bytes - o : chunk;
 			while ((int)e->out_ev.size() <= np) {
@@ -1472,9 +1480,13 @@ int download(fosphor_cu *e, const OutSeg *segs, int n)
 			pieces[np++] = {static_cast<char *>(segs[i].host) + o, off, nb};
 			off += nb;
 		}
+	}
 	for (int c = 0; c < np; c++) {
 		CU_CHECK(e, cudaEventSynchronize(e->out_ev[c]));
-		pool->copy(pieces[c].host, hp + pieces[c].off, pieces[c].bytes);
+		if (pool)
+			pool->copy(pieces[c].host, hp + pieces[c].off, pieces[c].bytes);
+		else
+			memcpy(pieces[c].host, hp + pieces[c].off, pieces[c].bytes);
 	}
 	CU_CHECK(e, cudaStreamSynchronize(e->stream));       /* cl.c:1052 */
 	return 0;
