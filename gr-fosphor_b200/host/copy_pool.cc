@@ -236,3 +236,37 @@ void copy_pool::copy(void *dst, const void *src, size_t bytes)
 }
 
 } /* namespace fosphor_b200 */
+
+/* C hook for the CPU test tier (tests/test_copy_pool.py): `rounds` jobs of `bytes` bytes in
+ * `pieces` pieces on a pool of `threads` workers, every piece checked the moment wait_piece()
+ * reports it, idle gaps long enough for the workers to fall asleep in between.  0 = all copies
+ * exact. */
+extern "C" int fosphor_host_copy_selftest(int threads, unsigned long long bytes, int pieces, int rounds)
+{
+	using fosphor_b200::copy_pool;
+	if (bytes == 0 || rounds < 1)
+		return -1;
+	copy_pool pool(threads);
+	std::vector<unsigned char> src(bytes), dst(bytes);
+	unsigned long long state = 0x9e3779b97f4a7c15ull;
+	for (int r = 0; r < rounds; r++) {
+		for (size_t i = 0; i < bytes; i += 61) {
+			state = state * 6364136223846793005ull + 1442695040888963407ull;
+			src[i] = (unsigned char)(state >> 56);
+		}
+		memset(dst.data(), 0, bytes);
+		pool.start(dst.data(), src.data(), bytes, pieces, (r & 1) != 0);
+		for (int p = 0; p < pieces; p++) {
+			pool.wait_piece(p);
+			const size_t off = pool.piece_offset(p);
+			if (off < bytes && memcmp(dst.data() + off, src.data() + off, pool.piece_size(p)) != 0)
+				return 1 + r;
+		}
+		if (memcmp(dst.data(), src.data(), bytes) != 0)
+			return 1 + r;
+		if (r % 7 == 3)
+			std::this_thread::sleep_for(std::chrono::milliseconds(6));   /* past the polling window: workers sleep */
+		pool.copy(dst.data(), src.data(), bytes / 3 + 1);
+	}
+	return 0;
+}

@@ -230,6 +230,10 @@ void  fosphor_fifo_write_commit(void *fifo, int size);
 void *fosphor_fifo_read_peek(void *fifo, int size, int wait);
 void  fosphor_fifo_read_discard(void *fifo, int size);
 
+/* Host-only self test of the staging copy pool (gr-fosphor_b200/host/copy_pool.h): jobs of `bytes`
+ * bytes in `pieces` in-order pieces on `threads` workers; 0 = every copy exact.  Needs no GPU. */
+int fosphor_host_copy_selftest(int threads, unsigned long long bytes, int pieces, int rounds);
+
 /* ------------------------------------------------------------------------ */
 /* 4. FFT window generator                                  */
 /* ------------------------------------------------------------------------ */

@@ -17,7 +17,7 @@ def _lib():
 
 def test_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "fosphor_b200.h")).read()
-    syms = sorted(set(re.findall(r"\b(fosphor_(?:cl|cu|fifo|window)_[a-z_]+)\s*\(", hdr)))
+    syms = sorted(set(re.findall(r"\b(fosphor_(?:cl|cu|fifo|window|host)_[a-z_]+)\s*\(", hdr)))
     assert len(syms) >= 25
     L = _lib()
     for s in syms:
