@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 
@@ -133,6 +134,42 @@ struct HostRange {             /* caller memory page-locked by the engine */
 	uintptr_t lo, hi;
 	std::vector<uint64_t> pfn; /* physical page numbers at registration (automatic mode), one per 4 KiB page */
 };
+
+/* Every range any engine of this process has page-locked.  cudaPointerGetAttributes cannot tell
+ * "page-locked by the caller" from "page-locked by another engine of this library" - and only the
+ * engine that registered a range can vouch for it (it holds the page numbers).  An engine that
+ * meets somebody else's registration stages instead of trusting it. */
+struct GlobalReg {
+	uintptr_t lo, hi;
+	const void *owner;
+};
+std::mutex g_reg_mutex;
+std::vector<GlobalReg> g_regs;
+
+void global_reg_add(const void *owner, uintptr_t lo, uintptr_t hi)
+{
+	std::lock_guard<std::mutex> lk(g_reg_mutex);
+	g_regs.push_back({lo, hi, owner});
+}
+
+void global_reg_remove(const void *owner, uintptr_t lo)
+{
+	std::lock_guard<std::mutex> lk(g_reg_mutex);
+	for (size_t i = 0; i < g_regs.size(); i++)
+		if (g_regs[i].owner == owner && g_regs[i].lo == lo) {
+			g_regs.erase(g_regs.begin() + (long)i);
+			return;
+		}
+}
+
+bool global_reg_foreign(const void *self, uintptr_t a, size_t bytes)
+{
+	std::lock_guard<std::mutex> lk(g_reg_mutex);
+	for (const GlobalReg &r : g_regs)
+		if (r.owner != self && a < r.hi && a + bytes > r.lo)
+			return true;
+	return false;
+}
 
 struct BatchTables {
 	int batch = -1;
@@ -1232,6 +1269,7 @@ uint64_t page_frame(fosphor_cu *e, uintptr_t addr)
 void hostreg_drop(fosphor_cu *e, size_t idx)
 {
 	HostRange &r = e->hostreg[idx];
+	global_reg_remove(e, r.lo);
 	if (cudaHostUnregister(reinterpret_cast<void *>(r.lo)) != cudaSuccess)
 		cudaGetLastError();
 	e->hostreg_bytes -= r.hi - r.lo;
@@ -1312,6 +1350,7 @@ bool hostreg_cover(fosphor_cu *e, const void *p, size_t bytes)
 	}
 	e->hostreg.push_back(std::move(nr));
 	e->hostreg_bytes += hi - lo;
+	global_reg_add(e, lo, hi);
 	return true;
 }
 
@@ -1327,6 +1366,8 @@ bool host_range_direct(fosphor_cu *e, const void *p, size_t bytes, size_t min_by
 			own = true;
 	if (own)
 		return hostreg_cover(e, p, bytes) && is_pinned_range(p, bytes);
+	if (global_reg_foreign(e, a, bytes))
+		return false;                        /* another engine's registration: only it can vouch for it */
 	if (is_pinned_range(p, bytes))
 		return true;                         /* page-locked by the caller (pinned FIFO, cudaHostRegister) */
 	return e->tn.hostreg != 0 && bytes >= min_bytes && hostreg_cover(e, p, bytes) && is_pinned_range(p, bytes);
@@ -1528,9 +1569,11 @@ void fosphor_cu_destroy(struct fosphor_cu *e)
 	if (e->stream)
 		cudaStreamSynchronize(e->stream);
 	e->pool.reset();
-	for (const HostRange &r : e->hostreg)
+	for (const HostRange &r : e->hostreg) {
+		global_reg_remove(e, r.lo);
 		if (cudaHostUnregister(reinterpret_cast<void *>(r.lo)) != cudaSuccess)
 			cudaGetLastError();
+	}
 	if (e->pagemap_fd >= 0)
 		close(e->pagemap_fd);
 	if (e->d_ring != e->d_wf)
@@ -1703,9 +1746,8 @@ int fosphor_cu_create(struct fosphor_cu **out, const struct fosphor_cu_params *p
 		}
 	}
 	{
-		/* fused kernel: narrow tiles so that N / cols CTAs fill the chip, and so that the state +
-		 * hit tiles of K > 512 bins leave room for a stage ring */
-		e->acc_cols = (p.fft_len <= 512 || p.n_bins > 1024) ? 4 : 8;
+		/* fused kernel: narrow tiles for short spectra so that N / cols CTAs still fill the chip */
+		e->acc_cols = p.fft_len <= 512 ? 4 : 8;
 		if (e->tn.acc_cols)
 			e->acc_cols = e->tn.acc_cols;
 		/* the tensor-map encoder lives in the driver and is fetched through the runtime */
