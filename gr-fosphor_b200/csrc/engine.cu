@@ -1257,6 +1257,10 @@ uint64_t page_frame(fosphor_cu *e, uintptr_t addr)
 		} else {
 			e->pagemap_fd = -1;
 		}
+		if (e->pagemap_fd == -1 && e->tn.hostreg < 0)
+			fprintf(stderr, "[+] fosphor_b200: pageable sample buffers are staged through copy threads (this process "
+			        "cannot read its page frame numbers, so page-locking them in place cannot be checked); set "
+			        "FOSPHOR_B200_HOSTREG=1 if the buffers outlive the engine (zero-copy DMA)\n");
 	}
 	if (e->pagemap_fd < 0)
 		return 0;
