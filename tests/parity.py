@@ -58,7 +58,8 @@ def check_waterfall(got, ref, rows=None):
         got, ref = got[rows], ref[rows]
     same = _eq_nonfinite(got, ref)
     assert np.all(np.isfinite(got) | same), "non-finite waterfall values differ"
-    d = np.where(same, 0.0, np.abs(got - ref))
+    with np.errstate(invalid="ignore"):          # inf - inf where both are the same infinity: masked by `same`
+        d = np.where(same, 0.0, np.abs(got - ref))
     mag_g, mag_r = 10.0 ** np.where(same, 0, got), 10.0 ** np.where(same, 0, ref)
     rowmax = np.maximum(mag_r.max(axis=-1, keepdims=True), 1e-300)
     ok = (d <= PWR_TOL) | (np.abs(mag_g - mag_r) <= MAG_REL_TOL * rowmax)
@@ -206,7 +207,8 @@ def check_spectrum(got, ref, cols=None, wf_ref=None, max_skipped=0, tol0=SPEC_TO
     if cols is not None:
         keep = keep & np.asarray(cols)[None, :]
     same = _eq_nonfinite(got, ref)
-    d = np.where(same, 0.0, np.abs(got - ref))
+    with np.errstate(invalid="ignore"):
+        d = np.where(same, 0.0, np.abs(got - ref))
     d = np.nan_to_num(d, nan=np.inf)
     assert np.all(d[:, :, 0] <= 1e-6), "x coordinates differ"
     excess = np.where(keep, d[:, :, 1] - tol, -1.0)
@@ -241,7 +243,8 @@ class DisplayTwin:
         ref_s = self.o.spectrum
         g = np.asarray(spectrum, np.float64)
         same = _eq_nonfinite(g, ref_s.astype(np.float64))
-        d = np.where(same, 0.0, np.abs(g - ref_s))
+        with np.errstate(invalid="ignore"):
+            d = np.where(same, 0.0, np.abs(g - ref_s))
         d = np.nan_to_num(d, nan=np.inf)
         assert d.max() <= TWIN_SPEC_TOL, "display stage on identical rows: live/max differ by %g" % d.max()
         return float(d.max())
