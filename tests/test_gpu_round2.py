@@ -323,3 +323,41 @@ def test_cfg4_channels_across_gpus_with_nccl_maxhold_reduce(torch_cuda):
     res = json.loads(line)
     assert res["n_gpus"] == world
     assert res["reduced_maxhold_is_elementwise_max"] is True
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_engine_parameters_display_stage_exact(torch_cuda, seed):
+    """Seeded random walk over the parameter space the ABI accepts - FFT size, bin count (odd ones
+    too), rise / decay / live constants, batch multiples of 1 / 8 / 16, call sequences that wrap the
+    ring - with the strongest check there is: the engine's histogram must equal, bit for bit, what the
+    oracle's display stage makes of the engine's own log-power rows (tier 1), and waterfall / flips /
+    histogram / live / max-hold must agree with the oracle end to end (tier 2)."""
+    from gr_fosphor_b200.engine import Fosphor
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([512, 1024, 2048, 4096, 8192, 16384]))
+    k = int(rng.choice([2, 3, 17, 64, 100, 128, 255, 256, 300, 512, 777, 1024]))
+    mult = int(rng.choice([1, 8, 16]))
+    w = int(rng.choice([256, 1024]))
+    cfg = dict(fft_len=n, n_bins=k, wf_rows=w, batch_mult=mult, batch_max=256,
+               t0r=float(rng.choice([4.0, 16.0, 50.0])), t0d=float(rng.choice([20.0, 256.0, 1024.0])),
+               alpha=float(rng.choice([0.002, 0.01, 0.1])))
+    max_units = max(1, (48 if n >= 8192 else 200) // mult)
+    sizes = [int(rng.integers(1, max_units + 1)) * mult for _ in range(int(rng.integers(2, 6)))]
+    x = signals.noise_tones(n * sum(sizes), n_fft=n, seed=2000 + seed, sigma=float(rng.choice([0.003, 0.02, 0.1])))
+    eng = Fosphor(**cfg)
+    orc = oracle_lib.Oracle(**cfg)
+    tw = parity.DisplayTwin(**cfg)
+    pos = 0
+    for s in sizes:
+        p0 = eng.waterfall_position
+        assert eng.process(x[pos:pos + s * n]) == 0 and orc.process(x[pos:pos + s * n]) == 0
+        _, host = eng.finish()
+        tw.feed(host["waterfall"], p0, s)
+        pos += s * n
+    orc.finish()
+    assert eng.waterfall_position == orc.waterfall_position == sum(sizes) % w
+    tw.check(host["histogram"], host["spectrum"])
+    sc, of = oracle_lib.power_range(n, 0, 10)
+    rows = np.arange(w) if sum(sizes) >= w else np.arange(sum(sizes))
+    parity.check_end_to_end(host, orc, rows, sum(sizes) * n, np.float32(sc) * np.float32(k), of)
+    eng.close()
