@@ -98,7 +98,7 @@ def count_flips(wf_got, wf_ref, hscale, hofs, n_bins, rows=None):
     return flips
 
 
-def check_histogram(got, ref, hits_in_play, flips=None, visible_hits=None, single_call=False):
+def check_histogram(got, ref, hits_in_play, flips=None, visible_hits=None, single_call=False, t0r=16.0):
     """flips: observed bin flips (count_flips) on `visible_hits` hits (default: all of
     hits_in_play); the out-of-tolerance cell budget is FLIP_BUDGET_X times that, scaled to the
     hits in play.  single_call: first call after the clears - strict +-1-bin adjacency rule."""
@@ -137,9 +137,10 @@ def check_histogram(got, ref, hits_in_play, flips=None, visible_hits=None, singl
         lone = badm & ~paired
         assert not lone.any(), "histogram: %d out-of-tolerance cells without an opposite-sign neighbour bin " \
             "(not a +-1-bin flip), first at %s" % (int(lone.sum()), np.argwhere(lone)[0])
-    # a flipped hit moves mass to the neighbouring bin only: column sums stay close
+    # a flipped hit moves mass to the neighbouring bin only: column sums stay close.  Not equal: the rise
+    # is (1 - hv) / t0r per hit, so a hit that leaves a saturated cell for an empty one adds up to 1 / t0r
     cs = np.abs(got.sum(axis=0) - ref.sum(axis=0))
-    assert cs.max() <= 0.05 + 1e-3 * ref.sum(axis=0).max(), "histogram column mass differs: %g" % cs.max()
+    assert cs.max() <= max(0.05, 1.5 / t0r) + 1e-3 * ref.sum(axis=0).max(), "histogram column mass differs: %g" % cs.max()
     return bad, float(d.max())
 
 
@@ -250,7 +251,7 @@ class DisplayTwin:
         return float(d.max())
 
 
-def check_end_to_end(host, ref, rows, hits_in_play, hscale, hofs, single_call=False, max_skipped=0):
+def check_end_to_end(host, ref, rows, hits_in_play, hscale, hofs, single_call=False, max_skipped=0, t0r=16.0):
     """Tier 2 in one call: `host` / `ref` are dicts (or objects) with waterfall, histogram,
     spectrum; `rows` the ring rows that hold data of the calls checked; hscale = scale * n_bins.
     Returns {"flips", "bad_cells", "hits"}."""
@@ -261,6 +262,6 @@ def check_end_to_end(host, ref, rows, hits_in_play, hscale, hofs, single_call=Fa
     check_waterfall(wf_h, wf_r, rows=rows)
     flips = count_flips(wf_h, wf_r, hscale, hofs, n_bins, rows=rows)
     bad, _ = check_histogram(g(host, "histogram"), g(ref, "histogram"), hits_in_play, flips=flips,
-                             visible_hits=len(rows) * wf_r.shape[1], single_call=single_call)
+                             visible_hits=len(rows) * wf_r.shape[1], single_call=single_call, t0r=t0r)
     check_spectrum(g(host, "spectrum"), g(ref, "spectrum"), wf_ref=wf_r[rows], max_skipped=max_skipped)
     return {"flips": flips, "bad_cells": bad, "hits": hits_in_play}

@@ -359,5 +359,5 @@ def test_random_engine_parameters_display_stage_exact(torch_cuda, seed):
     tw.check(host["histogram"], host["spectrum"])
     sc, of = oracle_lib.power_range(n, 0, 10)
     rows = np.arange(w) if sum(sizes) >= w else np.arange(sum(sizes))
-    parity.check_end_to_end(host, orc, rows, sum(sizes) * n, np.float32(sc) * np.float32(k), of)
+    parity.check_end_to_end(host, orc, rows, sum(sizes) * n, np.float32(sc) * np.float32(k), of, t0r=cfg["t0r"])
     eng.close()
