@@ -14,7 +14,9 @@ is `--passes` (default 50) passes over two alternating 3.2 GB input buffers, so 
 steps cover about a second of GPU time.  The waterfall has the reference's 1024 rows
 (cl.c:430-432); how many calls one launch pair folds is the engine's business (its log-power
 scratch ring), not the display's.  The timed region closes after fosphor_cu_flush() has joined
-the engine's accumulate stream.
+the engine's accumulate stream.  A second of this work holds the board at its power cap
+(clocks.reasons: sw_power_cap, SM clock ~1.55-1.65 GHz); `burst` is the same pass timed over 20 ms
+on a cool chip, before the cap bites.
 
 `e2e` (the headline against the reference arm) mirrors `--impl reference` exactly: the seven
 fosphor_cl_* symbols of the drop-in library, PAGEABLE host input as the unmodified sink hands
