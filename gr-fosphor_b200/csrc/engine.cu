@@ -1369,7 +1369,7 @@ bool host_range_direct(fosphor_cu *e, const void *p, size_t bytes, size_t min_by
 		if (a < r.hi && a + bytes > r.lo)
 			own = true;
 	if (own)
-		return hostreg_cover(e, p, bytes) && is_pinned_range(p, bytes);
+		return hostreg_cover(e, p, bytes);   /* inside one of this engine's own ranges (and re-validated): page-locked */
 	if (global_reg_foreign(e, a, bytes))
 		return false;                        /* another engine's registration: only it can vouch for it */
 	if (is_pinned_range(p, bytes))
@@ -1479,7 +1479,7 @@ int download(fosphor_cu *e, const OutSeg *segs, int n)
 	bool direct[8] = {};
 	size_t bounce = 0;
 	for (int i = 0; i < n && i < 8; i++) {
-		direct[i] = segs[i].bytes == 0 || host_range_direct(e, segs[i].host, segs[i].bytes, (size_t)256 << 10);
+		direct[i] = segs[i].bytes == 0 || host_range_direct(e, segs[i].host, segs[i].bytes, (size_t)8 << 10);
 		if (!direct[i])
 			bounce += segs[i].bytes;
 	}
