@@ -112,6 +112,17 @@ def test_c99_caller_builds_against_the_headers_and_fails_loudly_without_a_gpu(tm
     else:
         assert rc.returncode == 2, (rc.returncode, rc.stderr)
         assert "-EIO" in rc.stderr
+    # examples/dropin_bench.c: the host-fed sink-frame loop of bench.py's e2e arm, from plain C
+    exe2 = str(tmp_path / "dropin_bench")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-pedantic", "-D_POSIX_C_SOURCE=199309L",
+                           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "dropin_bench.c"),
+                           "-o", exe2, "-L", os.path.dirname(lib), "-lfosphor_b200",
+                           "-Wl,-rpath," + os.path.dirname(lib), "-lm"])
+    rc = subprocess.run([exe2, "3"], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert rc.returncode == 0 and "Msamples_per_s" in rc.stdout, rc.stderr
+    else:
+        assert rc.returncode == 2, (rc.returncode, rc.stderr)
 
 
 def test_reference_fosphor_c_links_against_the_dropin():
