@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 OUT=gpurun_out/r2_sanitizer.txt
 : > $OUT
-for tool in memcheck racecheck; do
+for tool in memcheck synccheck initcheck racecheck; do
   echo "== compute-sanitizer --tool $tool  (pytest -k 'cfg1_burst or n512_pairs or fallback_paths or validation_and_state')" >> $OUT
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 77 python -m pytest tests/test_gpu_engine_parity.py -m gpu -q -x -k "cfg1_burst or n512_pairs or fallback_paths or validation_and_state" > /tmp/san_$tool.log 2>&1
   echo "exit code $?" >> $OUT
