@@ -56,10 +56,10 @@ __attribute__((target("avx2"))) void copy_stream_avx2(char *d, const char *s, si
 constexpr size_t MIN_ITEM = 64 * 1024;
 /* how long an idle worker keeps polling before it sleeps: a streaming caller comes back every
  * 150-400 us (8 MiB per call at PCIe speed, a read-back in between); a sleeping worker costs
- * 50-100 us to wake, which was most of the staging time when this was 200 us.  With zero-copy input
- * the pool only moves the results of a frame (every ~1.6 ms at full rate): 4 ms keeps it awake
- * between frames (read-back 184 -> ~140 us) */
-constexpr auto SPIN_FOR = std::chrono::microseconds(4000);
+ * 50-100 us to wake, which was most of the staging time when this was 200 us (2.9 -> 5.1 Gsamples/s
+ * staged).  Longer windows (4 ms) measured no better and burn a core per worker in a sink that
+ * renders 30 frames a second */
+constexpr auto SPIN_FOR = std::chrono::microseconds(1500);
 } /* namespace */
 
 int copy_pool::default_threads()
