@@ -623,6 +623,12 @@ def run_e2e(torch, dist, dev, local, world, args, lib_path, FosphorCL, Fosphor, 
     one_thread, _ = dropin_frames(frame.ctypes.data, max(8, frames // 8),
                                   env={"FOSPHOR_B200_COPY_THREADS": "1", "FOSPHOR_B200_HOSTREG": "0"})
 
+    # BASELINE configs[0]: one 64k-sample burst (64 spectra) in, results out - a latency, not a throughput
+    try:
+        burst_lat = burst_latency(lambda: FosphorCL(lib_path), frame)
+    except Exception as ex:                                   # an extra; never lose the line over it
+        burst_lat = "failed: %r" % (ex,)
+
     # the parameterised engine from page-locked memory: 48 calls of K=256 + finish, and the raw stream
     k, calls = N_BINS, 48
     eng = Fosphor(fft_len=n, n_bins=k, wf_rows=WF_ROWS, device=local, stream=stream.cuda_stream)
@@ -651,6 +657,7 @@ def run_e2e(torch, dist, dev, local, world, args, lib_path, FosphorCL, Fosphor, 
                    "/proc/self/pagemap with PFNs, i.e. a privileged process such as this one: root=%s; otherwise "
                    "always staged)" % (os.geteuid() == 0),
             "pcie_GBps": v_page * 8e6 / 1e9 / world,
+            "cfg1_burst_latency_us": burst_lat,
             "variants": {
                 "dropin_pageable_default": v_page,
                 "dropin_pageable_always_staged": v_staged,
@@ -664,6 +671,23 @@ def run_e2e(torch, dist, dev, local, world, args, lib_path, FosphorCL, Fosphor, 
                          "callers that vouch for their buffers, like the sink with its long-lived FIFO); page_locked: "
                          "cudaHostAlloc'ed source (the pinned FIFO of SURVEY 8f#2); raw stream: "
                          "fosphor_cu_process_host_raw, hop=N/4, each raw sample crosses PCIe once"}}
+
+
+def burst_latency(make_engine, frame, reps=60):
+    """BASELINE configs[0] through the boundary: fosphor_cl_process(one 64-spectrum burst of 65536 samples) +
+    fosphor_cl_finish, host buffers in and out; median wall time in microseconds."""
+    eng = make_engine()
+    n = 64 * N_FFT
+    ts = []
+    for i in range(reps + 5):
+        t0 = time.perf_counter()
+        rc = eng.process_raw(frame.ctypes.data, n)
+        assert rc == 0, rc
+        assert eng.finish() == 1
+        if i >= 5:
+            ts.append((time.perf_counter() - t0) * 1e6)
+    eng.release()
+    return statistics.median(ts)
 
 
 def run_reference(args):
@@ -711,6 +735,19 @@ def run_reference(args):
         step()
     el = time.perf_counter() - t0
     value = args.steps * samples_per_step / el / 1e6
+    lat = None
+    if kind == "reference":
+        try:
+            ts = []
+            burst = np.ascontiguousarray(x[0][:64 * n])
+            for i in range(25):
+                t0 = time.perf_counter()
+                assert eng.process(burst) == 0 and eng.finish() == 1
+                if i >= 5:
+                    ts.append((time.perf_counter() - t0) * 1e6)
+            lat = statistics.median(ts)
+        except Exception as ex:
+            lat = "failed: %r" % (ex,)
     sample = ("%d steps of 8 calls x 1024 spectra + finish, %s" %
               (args.steps, "reference OpenCL kernels on the box's B200 via NVIDIA OpenCL (no CPU OpenCL platform exists), 128 bins"
                if kind == "reference" else "CPU oracle port, f32 FFT, all host threads, 128 bins"))
@@ -721,7 +758,8 @@ def run_reference(args):
            "config": CONFIG,
            "details": {"step": "one sink frame (config.e2e_frame); at N>1 rank 0 alone runs (one GPU busy)"},
            "cpu_baseline": {"value": value, "unit": "Mcomplex-samples/s", "cores": cores, "kind": kind, "sample": sample},
-           "e2e": {"value": value, "unit": "Mcomplex-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "e2e": {"value": value, "unit": "Mcomplex-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "cfg1_burst_latency_us": lat}
     if kind == "reference" and not args.no_cpu:
         # the box has no CPU OpenCL platform, so the reference's own kernels ran on the GPU; for a
         # host-cores figure next to it: the oracle port (same arithmetic, OpenMP), bounded sample
