@@ -75,6 +75,7 @@ struct AccumArgs {
 	float rho_rg;             /* fused kernel: (1-alpha)^(rows per warp step) */
 	int depth_log2;           /* fused kernel: log2 of the boxes in the stage ring */
 	int lut_staged;           /* update_kernel: the (d, e) table fits its shared memory (else read from global) */
+	int l2_hints;             /* fused kernel: rows are read for the last time (L2 evict-first) */
 };
 
 /* display.cl:161-165: bin = (int)round(histo_scale * (pwr + histo_ofs)), round
@@ -249,6 +250,13 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *tma
 {
 	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
 	             ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_hint(unsigned dst, const CUtensorMap *tmap, int c0, int c1, unsigned bar,
+                                                 unsigned long long pol)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+	             ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "l"(pol) : "memory");
 }
 
 constexpr int CNT_MAXBLK = 4;         /* row blocks whose partials are kept before a flush */
@@ -1025,14 +1033,20 @@ accumulate_fused_kernel(const AccumArgs a, const __grid_constant__ CUtensorMap t
 			const unsigned mask = (unsigned)a.wf_mask;
 			const unsigned total = (unsigned)a.n_calls * (unsigned)(B / BOXR);
 			const unsigned stage0 = cnt_smem_u32(stage);
+			unsigned long long pol = 0ull;
+			if (a.l2_hints)
+				asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
 			for (unsigned n = 0; n < total; n++) {
 				const unsigned slot = n & (DEPTH - 1u);
 				if (n >= DEPTH)
 					mbar_wait_parity(empty0 + 8u * slot, ((n >> dlog) - 1u) & 1u);
 				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
 				             ::"r"(full0 + 8u * slot), "r"((unsigned)C::BOX_BYTES) : "memory");
-				tma_load_2d(stage0 + slot * (unsigned)C::BOX_BYTES, &tmap, col0,
-				            (int)(((unsigned)a.wf_pos + n * BOXR) & mask), full0 + 8u * slot);
+				const int row = (int)(((unsigned)a.wf_pos + n * BOXR) & mask);
+				if (a.l2_hints)
+					tma_load_2d_hint(stage0 + slot * (unsigned)C::BOX_BYTES, &tmap, col0, row, full0 + 8u * slot, pol);
+				else
+					tma_load_2d(stage0 + slot * (unsigned)C::BOX_BYTES, &tmap, col0, row, full0 + 8u * slot);
 			}
 		}
 	}

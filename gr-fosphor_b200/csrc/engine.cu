@@ -85,6 +85,8 @@ struct Tuning {
 	int stage_piece_kb = 4096; /* STAGE_PIECE_KB: pageable sources are staged and DMA'd in pieces of about this size
 	                            * (1 / 2 / 4 / 8 MiB: 4.88 / 5.15 / 5.30 / 5.31 Gsamples/s with a finish per frame) */
 	int stage_slots = 0;       /* STAGE_SLOTS: staging slots (0 = 4, or 2 when a slot is larger than 32 MiB) */
+	int l2_hints = 0;          /* L2_HINTS: N <= 1024 stream kernel reads samples evict-first and writes log-power rows
+	                            * evict-last; the fused accumulate kernel reads them evict-first */
 };
 
 int env_int(const char *name, int dflt)
@@ -126,6 +128,7 @@ Tuning tuning_from_env()
 	t.stage_piece_kb = env_int("STAGE_PIECE_KB", t.stage_piece_kb);
 	if (t.stage_piece_kb < 64) t.stage_piece_kb = 64;
 	t.stage_slots = env_int("STAGE_SLOTS", t.stage_slots);
+	t.l2_hints = env_int("L2_HINTS", t.l2_hints) != 0;
 	if (t.stage_slots < 0 || t.stage_slots > MAX_STAGE_SLOTS) t.stage_slots = 0;
 	return t;
 }
@@ -508,10 +511,10 @@ cudaError_t stream_launch(fosphor_cu *e, const float2 *in, long long hop, int wf
 	prof_mark(e, 0, 0);
 	if (e->tn.fft_variant >= 2)
 		fft_power_stream_kernel<P, true><<<grid, C::THREADS, C::SMEM_TWREG, e->stream>>>(
-			in, hop, e->d_win, e->d_tw, e->d_ring, wf_pos, e->ring_rows - 1, n_spectra);
+			in, hop, e->d_win, e->d_tw, e->d_ring, wf_pos, e->ring_rows - 1, n_spectra, e->tn.l2_hints);
 	else
 		fft_power_stream_kernel<P, false><<<grid, C::THREADS, C::SMEM, e->stream>>>(
-			in, hop, e->d_win, e->d_tw, e->d_ring, wf_pos, e->ring_rows - 1, n_spectra);
+			in, hop, e->d_win, e->d_tw, e->d_ring, wf_pos, e->ring_rows - 1, n_spectra, e->tn.l2_hints);
 	prof_mark(e, 0, 1);
 	e->launches++;
 	return cudaGetLastError();
@@ -837,6 +840,7 @@ cudaError_t fused_launch(fosphor_cu *e, AccumArgs a, cudaStream_t st)
 	while (dlog > 0 && (1ll << (dlog - 1)) >= boxes)
 		dlog--;
 	a.depth_log2 = dlog;
+	a.l2_hints = e->tn.l2_hints;
 	if constexpr (LOAD != 0) {
 		/* parity waits on the stage ring are only sound for these shapes (accumulate.cuh: acc_ring_safe) */
 		if (!acc_ring_safe(1ll << dlog, (long long)GC * (a.batch / BOXR), boxes))

@@ -262,6 +262,34 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
 	             ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+/* L2 residency hints (engine knob L2_HINTS): samples are read once (evict first), log-power rows are
+ * read again by the accumulate kernel a chunk later (evict last) */
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+	unsigned long long p;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+	unsigned long long p;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+
+__device__ __forceinline__ void bulk_g2s_hint(unsigned dst, const void *src, unsigned bytes, unsigned bar,
+                                              unsigned long long pol)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+	             ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ void st_f32_hint(float *p, float v, unsigned long long pol)
+{
+	asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+
 template <class P>
 struct StreamCfg {
 	static_assert(P::NPASS == 2 && P::T == 32, "one warp per spectrum plans only");
@@ -287,7 +315,7 @@ template <class P, bool TWREG>
 __global__ void __launch_bounds__(StreamCfg<P>::THREADS, StreamCfg<P>::CTAS_PER_SM)
 fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
                         const float *__restrict__ win, const float2 *__restrict__ tw,
-                        float *__restrict__ wf, int wf_pos, int wf_mask, int n_spectra)
+                        float *__restrict__ wf, int wf_pos, int wf_mask, int n_spectra, int l2_hints)
 {
 	using C = StreamCfg<P>;
 	constexpr int N = P::N, R0 = P::R0, R1 = P::R1;
@@ -295,6 +323,8 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int gw = blockIdx.x * C::WARPS + warp;
+	const unsigned long long pol_in = l2_hints ? l2_policy_evict_first() : 0ull;
+	const unsigned long long pol_out = l2_hints ? l2_policy_evict_last() : 0ull;
 	const int G = gridDim.x * C::WARPS;
 
 	float2 *bufs = reinterpret_cast<float2 *>(smem_raw) + (size_t)warp * 2 * C::BUF_ELEMS;
@@ -342,9 +372,13 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 		const int s0 = u * SPW;
 		const int nv = n_spectra - s0 < SPW ? n_spectra - s0 : SPW;
 		mbar_expect_tx(bar0 + 8 * slot, C::IN_BYTES * (unsigned)nv);
-		for (int q = 0; q < nv; q++)
-			bulk_g2s(buf0 + slot * BUF_BYTES + (unsigned)q * (unsigned)(sizeof(float2) * P::SM_ELEMS),
-			         in + (long long)(s0 + q) * hop, C::IN_BYTES, bar0 + 8 * slot);
+		for (int q = 0; q < nv; q++) {
+			const unsigned dst = buf0 + slot * BUF_BYTES + (unsigned)q * (unsigned)(sizeof(float2) * P::SM_ELEMS);
+			if (l2_hints)
+				bulk_g2s_hint(dst, in + (long long)(s0 + q) * hop, C::IN_BYTES, bar0 + 8 * slot, pol_in);
+			else
+				bulk_g2s(dst, in + (long long)(s0 + q) * hop, C::IN_BYTES, bar0 + 8 * slot);
+		}
 	};
 
 	int u = gw;
@@ -409,10 +443,17 @@ fft_power_stream_kernel(const float2 *__restrict__ in, long long hop,
 				v[t] = cmul(v[t], TWREG ? twreg[t] : __ldg(&tw[t * R0 + k]));
 			dif<R1>(v);
 			if (s < n_spectra) {
-				static_for<0, R1>([&](auto tc) {
-					constexpr int t = decltype(tc)::value;
-					row[i1 + t * P::NB1] = log_power(v[brev<R1>(t)]);
-				});
+				if (l2_hints) {
+					static_for<0, R1>([&](auto tc) {
+						constexpr int t = decltype(tc)::value;
+						st_f32_hint(&row[i1 + t * P::NB1], log_power(v[brev<R1>(t)]), pol_out);
+					});
+				} else {
+					static_for<0, R1>([&](auto tc) {
+						constexpr int t = decltype(tc)::value;
+						row[i1 + t * P::NB1] = log_power(v[brev<R1>(t)]);
+					});
+				}
 			}
 		}
 	}

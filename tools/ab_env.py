@@ -45,10 +45,12 @@ def main():
         bufs.append(x)
     first = None
     for var in variants:
-        for key, v in var.items():
+        env = {key: v for key, v in var.items() if key != "SCRATCH"}      # SCRATCH: the scratch_rows parameter
+        for key, v in env.items():
             os.environ["FOSPHOR_B200_" + key] = v
-        eng = Fosphor(fft_len=n, n_bins=k, wf_rows=1024, stream=stream.cuda_stream)
-        for key in var:
+        eng = Fosphor(fft_len=n, n_bins=k, wf_rows=1024, stream=stream.cuda_stream,
+                      scratch_rows=int(var.get("SCRATCH", 0)))
+        for key in env:
             os.environ.pop("FOSPHOR_B200_" + key)
         for i in range(4):
             eng.process_device_multi(bufs[i % 2].data_ptr(), calls, b, hop)
